@@ -1,0 +1,156 @@
+/*
+ * pdg_b200.h -- C-ABI of libpdg_b200.so: the B200 (sm_100a) implementation of parallelDG's
+ * parallel Metropolis-Hastings hot path, many independent chains at once.
+ *
+ * This is the drop-in boundary.  The reference is pure Python and has no FFI; each entry point
+ * below names the reference interface it replaces (paths under /root/reference/parallelDG/).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative PDG_E_* code; pdg_last_error() gives the
+ *     message of the last failure on that context.  Nothing throws across the ABI.
+ *   - `const void *` inputs may be HOST or DEVICE pointers (resolved with UVA /
+ *     cudaMemcpyDefault); outputs are written to caller-owned HOST or DEVICE buffers.
+ *   - the caller owns every buffer it passes in; the library owns only its internal device state.
+ *   - one context = one GPU + one stream; calls on a context are not re-entrant.  One context
+ *     per GPU, driven by one host thread/process per GPU (replaces process-per-chain,
+ *     mh_parallel.py:479-530).
+ *   - bitsets are W = ceil(p/64) little-endian 64-bit words, bit g of word g/64.
+ *   - a chain's state is the reference's JunctionMap (graph/junction_tree.py:11-132): a tree on
+ *     p tree nodes (p-1 edges) and one clique bitset per tree node.
+ */
+#ifndef PDG_B200_H
+#define PDG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDG_ABI_VERSION 1
+
+enum pdg_error {
+    PDG_OK = 0,
+    PDG_E_ARG = -1,          /* bad argument */
+    PDG_E_CUDA = -2,         /* CUDA runtime error */
+    PDG_E_STATE = -3,        /* call order (model/state not set) */
+    PDG_E_REPLAY = -4,       /* replay log disagrees with the enumerated move set */
+    PDG_E_OVERFLOW = -5,     /* update-record capacity exceeded */
+    PDG_E_NUMERIC = -6,      /* non-positive pivot / unsupported clique size */
+    PDG_E_NOMEM = -7
+};
+
+enum pdg_model_kind { PDG_MODEL_UNIFORM = 0, PDG_MODEL_GGM = 1, PDG_MODEL_LOGLIN = 2 };
+/* mh_parallel.py:317-332 get_prior */
+enum pdg_prior_kind { PDG_PRIOR_MBC = 0, PDG_PRIOR_EDGEPENALTY = 1, PDG_PRIOR_JUMPPENALTY = 2, PDG_PRIOR_UNIFORM = 3 };
+/* mh_parallel.py:182-315 (parallel moves) / :23-180 (single move) */
+enum pdg_kernel_kind { PDG_KIND_PARALLEL = 0, PDG_KIND_SINGLE = 1 };
+
+typedef struct pdg_ctx pdg_ctx;
+
+/* one accepted move = one entry of Trajectory.jt_updates (mh_parallel.py:270,302):
+ * (i, k, move_type, {node}, (Cnew, C, Cadj)); C and Cadj travel as bitsets next to the header,
+ * Cnew = C +/- node. */
+typedef struct pdg_update {
+    int32_t i;        /* MCMC index */
+    int32_t k;        /* proposal sub-index */
+    uint16_t node;    /* graph vertex moved */
+    uint16_t U;       /* tree node whose clique changed */
+    int16_t Uadj;     /* anchor tree node, -1 = none */
+    uint8_t type;     /* 0 connect, 1 disconnect */
+    uint8_t pad;
+} pdg_update;
+
+/* replay of the reference's random streams; arrays for ALL chains of the
+ * context, chain-major.  HOST or DEVICE pointers. */
+typedef struct pdg_replay {
+    int64_t n_samples;        /* stride of the it_* arrays */
+    const int32_t *it_node;   /* [n_chains][n_samples] np.random.randint(p)   (mh_parallel.py:230) */
+    const int32_t *it_mtype;  /* [n_chains][n_samples] np.random.randint(2)   (:231) */
+    const int32_t *it_aux;    /* [n_chains][n_samples] random tree node (pm:138) / random leaf (pm:185), else -1 */
+    const int64_t *it_off;    /* [n_chains][n_samples+1] offsets into the mv_* arrays */
+    const int32_t *mv_U;      /* ordered proposals of every iteration */
+    const int32_t *mv_Uadj;
+    const double *mv_u;       /* np.random.uniform() per proposal (:268,:300) */
+    int64_t n_moves_total;
+} pdg_replay;
+
+int pdg_abi_version(void);
+
+/* replaces: the per-chain set-up of sample_trajectory (mh_parallel.py:188-223).
+ * chain ids chain0 .. chain0+n_chains-1 select the Philox streams (so shards on different GPUs
+ * draw different chains); rec_cap = update records kept per chain. */
+int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chain0,
+               uint64_t seed, int64_t n_samples, int64_t rec_cap);
+int pdg_destroy(pdg_ctx *ctx);
+const char *pdg_last_error(pdg_ctx *ctx);
+/* the stream every later call is enqueued on (0 = default); a cudaStream_t passed as void* */
+int pdg_set_stream(pdg_ctx *ctx, void *stream);
+
+/* replaces: get_prior (mh_parallel.py:317-332) + seqdist priors (:31-151) */
+int pdg_set_prior(pdg_ctx *ctx, int prior_kind, double a, double b);
+/* replaces: UniformJTDistribution (seqdist:154-176) */
+int pdg_set_model_uniform(pdg_ctx *ctx);
+/* replaces: GGMJTPosterior.init_model (seqdist:334-343).  A = D + X^T X and D are p*p row-major
+ * fp64; gconst[k], k = 0..p, holds the Gamma-function part of the clique score
+ * (wishart.py:24-30):  (-t1 k log(pi) + multigammaln(t1,k)) - (-t2 k log(pi) + multigammaln(t2,k)),
+ * t1 = (delta+n+k-1)/2, t2 = (delta+k-1)/2, gconst[0] = 0. */
+int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, double delta,
+                      const void *gconst);
+/* replaces: LogLinearJTPosterior.init_model (seqdist:239-252).  data: column-major level codes
+ * [p][nrows] uint8; levels[p]; lgtab (nullable): [n_ktab][nrows+1] fp64 with
+ * lgtab[j][c] = lgamma(c + alpha_j) - lgamma(alpha_j) for the j-th distinct cell count
+ * ktab[j] = prod of levels over a set (dirichlet.py:76-83), alpha_j = alphatab[j]
+ * (loglin:52-55); when NULL the device lgamma is used. */
+int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int64_t nrows,
+                         double cell_alpha, int n_ktab, const void *ktab, const void *alphatab,
+                         const void *lgtab);
+
+/* replaces: JunctionMap.__init__ from a junction tree (junction_tree.py:12-76).
+ * edges [count][p-1][2] int32, bits [count][p][W] uint64 */
+int pdg_set_state(pdg_ctx *ctx, int64_t chain_begin, int64_t chain_count, const void *edges,
+                  const void *bits);
+int pdg_get_state(pdg_ctx *ctx, int64_t chain_begin, int64_t chain_count, void *edges, void *bits);
+/* every chain starts from the same decomposable graph given by its maximal cliques
+ * (mh_parallel.py:190-192), or from p singletons when bits == NULL (:194-200); follow with
+ * pdg_randomize(ctx, 0) to draw the per-chain junction tree + labelling. */
+int pdg_set_cliques(pdg_ctx *ctx, const void *bits, int n_cliques);
+/* replaces: JunctionMap.randomize_by_jt (junction_tree.py:235-241) for every chain */
+int pdg_randomize(pdg_ctx *ctx, uint32_t iter);
+/* replaces: logl[0] (mh_parallel.py:59-60 / :217-218) */
+int pdg_init_logl(pdg_ctx *ctx, int kind);
+/* replaces: the loop body of sample_trajectory / sample_trajectory_single_move for MCMC
+ * indices [it_begin, it_end) with no randomisation inside; replay == NULL -> Philox streams */
+int pdg_run(pdg_ctx *ctx, int kind, int64_t it_begin, int64_t it_end, const pdg_replay *replay);
+/* replaces: sample_trajectory(n_samples, randomize, ...) end to end in Philox mode:
+ * init_logl, then for every block of `randomize` iterations randomise + run */
+int pdg_sample(pdg_ctx *ctx, int kind, int64_t randomize);
+/* waits for the context's stream and reports the first per-chain error, if any */
+int pdg_sync(pdg_ctx *ctx);
+
+/* outputs (Trajectory fields: n_updates, logl, jt_updates) */
+int pdg_get_counts(pdg_ctx *ctx, void *n_proposals /*int64[n_chains]*/, void *n_accepted /*int64[n_chains]*/);
+int pdg_get_logl(pdg_ctx *ctx, void *logl /* double[n_chains][n_samples] */);
+/* trajectory compaction: packs the per-chain update records contiguously on the device;
+ * total = number of records, offsets[n_chains+1] (nullable) */
+int pdg_compact_updates(pdg_ctx *ctx, int64_t *total, void *offsets);
+int pdg_get_updates(pdg_ctx *ctx, void *updates /* pdg_update[total] */, void *bits /* uint64[total][2][W] */);
+/* per-proposal diagnostics of the LAST pdg_run (only when enabled): k-indexed, chain-major
+ * [n_chains][cap]: dlik, dprior, logq, u (fp64) and acc (int32) */
+int pdg_enable_move_log(pdg_ctx *ctx, int64_t cap_per_chain);
+int pdg_get_move_log(pdg_ctx *ctx, void *dlik, void *dprior, void *logq, void *u, void *acc, void *U);
+
+/* replaces: sd.log_likelihood_partial([c], {}) for a batch of complete sets
+ * (ggm:42-86 / loglin:39-70): bits [n_sets][W] -> scores[n_sets] */
+int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores);
+/* edge-inclusion tallies (trajectory.py:126-152 + empirical_graph_distribution.py:35-41):
+ * tallies[p][p] int64 += sum over chains and MCMC indices >= burnin of the edge indicator */
+int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies);
+
+/* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t pdg_launch_count(pdg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,305 @@
+// Junction-tree randomisation, one warp per chain.  Restates JunctionMap.randomize_by_jt
+// (junction_tree.py:235-241): graph from cliques (:201-219) -> maximal cliques + a junction tree
+// (decomposable.py:124-150, here by maximum-cardinality search) -> uniform random equivalent
+// junction tree (junction_tree.py:698-774; every distinct separator handled from the original
+// tree, Thomas & Green 2009) -> random relabelling + empty-node padding (:19-65).  All draws come
+// from addressable Philox streams, so lanes generate them in parallel.
+#pragma once
+#include "pdg_kernels.cuh"
+
+struct RandSmem {
+    int off_card, off_order, off_cliqueof, off_parent, off_keys, off_jdraw, off_comp, off_nodes, off_rank,
+        off_cstart, off_canon, off_compidx, off_vind, off_wj, off_cnt, off_fill, off_off, off_newe,
+        off_done, off_inT, off_inw, off_isroot, off_numbered, off_used, off_X, total;
+};
+
+__host__ __device__ inline RandSmem rand_smem_layout(int p, int W)
+{
+    RandSmem s;
+    int o = 0;
+    const int a2 = (((p + 2) * 2 + 15) / 16) * 16, a1 = ((p + 2 + 15) / 16) * 16;
+    s.off_card = o; o += a2;   s.off_order = o; o += a2;  s.off_cliqueof = o; o += a2;
+    s.off_parent = o; o += a2; s.off_keys = o; o += a2;   s.off_jdraw = o; o += a2;
+    s.off_comp = o; o += a2;   s.off_nodes = o; o += a2;  s.off_rank = o; o += a2;
+    s.off_cstart = o; o += a2; s.off_canon = o; o += a2;  s.off_compidx = o; o += a2;
+    s.off_vind = o; o += a2;   s.off_wj = o; o += a2;     s.off_cnt = o; o += a2;
+    s.off_fill = o; o += a2;   s.off_off = o; o += a2;    s.off_newe = o; o += 2 * a2;
+    s.off_done = o; o += a1;   s.off_inT = o; o += a1;    s.off_inw = o; o += a1;  s.off_isroot = o; o += a1;
+    s.off_numbered = o; o += W * 8; s.off_used = o; o += W * 8; s.off_X = o; o += W * 8;
+    s.total = o;
+    return s;
+}
+
+struct RandScratch {
+    u64 *adj, *K, *sep;   // [chain][p][W] each
+};
+
+__device__ __forceinline__ bool subset_w(const u64 *a, const u64 *b, int W)
+{
+    for (int w = 0; w < W; ++w) if (a[w] & ~b[w]) return false;
+    return true;
+}
+__device__ __forceinline__ bool equal_w(const u64 *a, const u64 *b, int W)
+{
+    for (int w = 0; w < W; ++w) if (a[w] != b[w]) return false;
+    return true;
+}
+
+// derived state of one chain: N = transpose of M, CSR of the tree.  Called by one warp.
+__device__ __forceinline__ void build_derived(const PdgParams &P, long long chain, int lane,
+                                              unsigned short *s_off, unsigned short *s_fill)
+{
+    const int p = P.p, W = P.W;
+    u64 *Mc = P.M + (size_t)chain * p * W;
+    u64 *Nc = P.N + (size_t)chain * p * W;
+    const int *E = P.edges + (size_t)chain * 2 * (p - 1);
+    for (int i = lane; i < p * W; i += 32) Nc[i] = 0ull;
+    for (int i = lane; i <= p; i += 32) { s_off[i] = 0; s_fill[i] = 0; }
+    __syncwarp();
+    for (int i = lane; i < p * W; i += 32) {
+        const int t = i / W, w = i - t * W;
+        u64 x = Mc[i];
+        while (x) {
+            const int b = __ffsll((long long)x) - 1;
+            x &= x - 1;
+            const int g = w * 64 + b;
+            atomicOr(&Nc[(size_t)g * W + (t >> 6)], 1ull << (t & 63));
+        }
+    }
+    // degree histogram through 32-bit shared atomics on packed halves is awkward; the tree is
+    // tiny, so count with per-lane passes over the edge list instead
+    for (int t = lane; t < p; t += 32) {
+        int d = 0;
+        for (int e = 0; e < p - 1; ++e) d += (E[2 * e] == t) + (E[2 * e + 1] == t);
+        s_fill[t] = (unsigned short)d;
+    }
+    __syncwarp();
+    if (lane == 0) { int acc = 0; for (int t = 0; t < p; ++t) { s_off[t] = (unsigned short)acc; acc += s_fill[t]; } s_off[p] = (unsigned short)acc; }
+    __syncwarp();
+    unsigned short *g_off = P.csr_off + (size_t)chain * (p + 1);
+    unsigned short *g_adj = P.csr_adj + (size_t)chain * 2 * p;
+    for (int t = lane; t <= p; t += 32) g_off[t] = s_off[t];
+    for (int t = lane; t < p; t += 32) {
+        int o = s_off[t];
+        for (int e = 0; e < p - 1; ++e) {
+            const int a = E[2 * e], b = E[2 * e + 1];
+            if (a == t) g_adj[o++] = (unsigned short)b;
+            else if (b == t) g_adj[o++] = (unsigned short)a;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long chain_begin, long long chain_count)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const long long c = blockIdx.x;
+    if (c >= chain_count) return;
+    unsigned short *s_off = (unsigned short *)smem;
+    unsigned short *s_fill = s_off + (P.p + 2);
+    build_derived(P, chain_begin + c, threadIdx.x, s_off, s_fill);
+}
+
+__global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u32 iter)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int p = P.p, W = P.W, lane = threadIdx.x;
+    const long long chain = blockIdx.x;
+    const RandSmem L = rand_smem_layout(p, W);
+    unsigned short *card = (unsigned short *)(smem + L.off_card), *order = (unsigned short *)(smem + L.off_order);
+    unsigned short *cliqueof = (unsigned short *)(smem + L.off_cliqueof), *keys = (unsigned short *)(smem + L.off_keys);
+    short *parent = (short *)(smem + L.off_parent);
+    unsigned short *jdraw = (unsigned short *)(smem + L.off_jdraw), *comp = (unsigned short *)(smem + L.off_comp);
+    unsigned short *nodes = (unsigned short *)(smem + L.off_nodes), *rank = (unsigned short *)(smem + L.off_rank);
+    unsigned short *cstart = (unsigned short *)(smem + L.off_cstart), *canon = (unsigned short *)(smem + L.off_canon);
+    unsigned short *compidx = (unsigned short *)(smem + L.off_compidx), *vind = (unsigned short *)(smem + L.off_vind);
+    unsigned short *wj = (unsigned short *)(smem + L.off_wj), *cnt = (unsigned short *)(smem + L.off_cnt);
+    unsigned short *fill = (unsigned short *)(smem + L.off_fill), *s_off = (unsigned short *)(smem + L.off_off);
+    unsigned short *newe = (unsigned short *)(smem + L.off_newe);
+    unsigned char *done = smem + L.off_done, *inT = smem + L.off_inT, *inw = smem + L.off_inw, *isroot = smem + L.off_isroot;
+    u64 *numbered = (u64 *)(smem + L.off_numbered), *used = (u64 *)(smem + L.off_used), *X = (u64 *)(smem + L.off_X);
+    u64 *Mc = P.M + (size_t)chain * p * W;
+    const u64 *Nc = P.N + (size_t)chain * p * W;
+    u64 *adj = Z.adj + (size_t)chain * p * W, *K = Z.K + (size_t)chain * p * W, *sep = Z.sep + (size_t)chain * p * W;
+    int *E = P.edges + (size_t)chain * 2 * (p - 1);
+    const u32 gchain = P.chain0 + (u32)chain, k0 = P.seed_lo, k1 = P.seed_hi;
+
+    // ---- (a) graph adjacency: adj[v] = union of the cliques holding v, minus v (:201-219) ----
+    for (int i = lane; i < p * W; i += 32) {
+        const int v = i / W, w = i - v * W;
+        u64 acc = 0ull;
+        for (int tw = 0; tw < W; ++tw) {
+            u64 x = Nc[(size_t)v * W + tw];
+            while (x) {
+                const int b = __ffsll((long long)x) - 1;
+                x &= x - 1;
+                acc |= Mc[(size_t)(tw * 64 + b) * W + w];
+            }
+        }
+        if ((v >> 6) == w) acc &= ~(1ull << (v & 63));
+        adj[i] = acc;
+        K[i] = 0ull; sep[i] = 0ull;
+    }
+    for (int i = lane; i < p; i += 32) { card[i] = 0; done[i] = 0; inT[i] = 0; }
+    if (lane < W) { numbered[lane] = 0ull; used[lane] = 0ull; }
+    __syncwarp();
+
+    // ---- (b) maximum cardinality search -> cliques K[0..S), parent[], sep[] ----------------
+    int S = 0, prev_card = 0;
+    for (int step = 0; step < p; ++step) {
+        u32 best = 0u;
+        for (int u = lane; u < p; u += 32)
+            if (!bit64(numbered, u)) { const u32 key = ((u32)card[u] << 16) | (u32)(0xFFFFu - u); best = key > best ? key : best; }
+        best = __reduce_max_sync(PDG_FULL, best);
+        const int v = (int)(0xFFFFu - (best & 0xFFFFu)), new_card = (int)(best >> 16);
+        if (new_card <= prev_card) {
+            u32 lastkey = 0u;
+            if (lane < W) {
+                const u64 x0 = adj[(size_t)v * W + lane] & numbered[lane];
+                K[(size_t)S * W + lane] = x0; sep[(size_t)S * W + lane] = x0;
+                u64 x = x0;
+                while (x) {
+                    const int b = __ffsll((long long)x) - 1;
+                    x &= x - 1;
+                    const int g = lane * 64 + b;
+                    const u32 key = ((u32)order[g] << 16) | (u32)g;
+                    lastkey = key > lastkey ? key : lastkey;
+                }
+            }
+            lastkey = __reduce_max_sync(PDG_FULL, lastkey);
+            if (lane == 0) parent[S] = (new_card != 0) ? (short)cliqueof[lastkey & 0xFFFFu] : (short)(S == 0 ? -1 : 0);
+            ++S;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            cliqueof[v] = (unsigned short)(S - 1);
+            K[(size_t)(S - 1) * W + (v >> 6)] |= 1ull << (v & 63);
+            order[v] = (unsigned short)step;
+        }
+        if (lane < W) {
+            u64 x = adj[(size_t)v * W + lane] & ~numbered[lane];
+            if ((v >> 6) == lane) { numbered[lane] |= 1ull << (v & 63); }
+            while (x) {
+                const int b = __ffsll((long long)x) - 1;
+                x &= x - 1;
+                card[lane * 64 + b] += 1;
+            }
+        }
+        prev_card = new_card;
+        __syncwarp();
+    }
+
+    // ---- (c) every distinct separator: components of the induced forest + generalised Pruefer
+    int ne = 0;
+    for (int c = 1; c < S; ++c) {
+        if (done[c]) continue;           // warp-uniform (shared memory)
+        if (lane < W) X[lane] = sep[(size_t)c * W + lane];
+        __syncwarp();
+        int P_ = 0, q = 0;
+        for (int base = 0; base < S; base += 32) {
+            const int d = base + lane;
+            bool in = false, root = false, dn = false;
+            if (d < S) {
+                in = subset_w(X, K + (size_t)d * W, W);
+                if (in) {
+                    const int pd = parent[d];
+                    const bool top = (pd < 0) || !subset_w(X, K + (size_t)pd * W, W);
+                    const bool eq = (d > 0) && equal_w(sep + (size_t)d * W, X, W);
+                    root = top || eq;
+                    dn = !top && eq;
+                }
+            }
+            const u32 bin = __ballot_sync(PDG_FULL, in), broot = __ballot_sync(PDG_FULL, root);
+            if (in) {
+                nodes[P_ + __popc(bin & ((1u << lane) - 1u))] = (unsigned short)d;
+                inT[d] = 1; isroot[d] = root ? 1 : 0;
+                if (dn) done[d] = 1;
+                if (root) rank[d] = (unsigned short)(q + __popc(broot & ((1u << lane) - 1u)));
+            }
+            P_ += __popc(bin); q += __popc(broot);
+        }
+        __syncwarp();
+        for (int i = lane; i <= q; i += 32) { cstart[i] = 0; }
+        for (int i = lane; i < q; i += 32) { cnt[i] = 0; inw[i] = 1; fill[i] = 0; }
+        __syncwarp();
+        if (lane == 0) {
+            for (int a = 0; a < P_; ++a) {
+                const int d = nodes[a];
+                comp[d] = isroot[d] ? (unsigned short)d : comp[parent[d]];
+                cstart[rank[comp[d]] + 1] += 1;
+            }
+            for (int i = 0; i < q; ++i) cstart[i + 1] += cstart[i];
+            for (int a = 0; a < P_; ++a) {
+                const int d = nodes[a], i = rank[comp[d]];
+                const int pos = cstart[i] + fill[i]++;
+                canon[pos] = (unsigned short)d; compidx[pos] = (unsigned short)i;
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < q - 2; t += 32)
+            vind[t] = (unsigned short)draw_int(k0, k1, gchain, iter, TAG_PRUF_V, ((u32)c << 16) | (u32)t, (u32)P_);
+        for (int i = lane; i < q; i += 32)
+            wj[i] = (unsigned short)draw_int(k0, k1, gchain, iter, TAG_PRUF_W, ((u32)c << 16) | (u32)i, (u32)(cstart[i + 1] - cstart[i]));
+        __syncwarp();
+        if (lane == 0) {
+            // junction_tree.py:749-769 with a descending pointer instead of the rescans
+            for (int t = 0; t < q - 2; ++t) cnt[compidx[vind[t]]] += 1;
+            int ptr = q - 1, pending = -1;
+            for (int t = q - 3; t >= 0; --t) {
+                int x;
+                if (pending >= 0) { x = pending; pending = -1; }
+                else { while (!(inw[ptr] && cnt[ptr] == 0)) --ptr; x = ptr; }
+                const int y = vind[t], cy = compidx[y];
+                newe[2 * ne] = canon[cstart[x] + wj[x]]; newe[2 * ne + 1] = canon[y]; ++ne;
+                inw[x] = 0;
+                cnt[cy] -= 1;
+                if (cnt[cy] == 0 && inw[cy] && cy > ptr) pending = cy;
+            }
+            int a = -1, b = -1;
+            for (int i = 0; i < q; ++i) if (inw[i]) { if (a < 0) a = i; else if (b < 0) b = i; }
+            newe[2 * ne] = canon[cstart[a] + wj[a]]; newe[2 * ne + 1] = canon[cstart[b] + wj[b]]; ++ne;
+        }
+        ne = __shfl_sync(PDG_FULL, ne, 0);
+        for (int a = lane; a < P_; a += 32) inT[nodes[a]] = 0;
+        __syncwarp();
+    }
+    if (ne != (S > 0 ? S - 1 : 0)) { if (lane == 0) atomicOr(&P.err[chain], ERR_NUMERIC); }
+
+    // ---- (d) relabel + pad (junction_tree.py:36-64) ------------------------------------------
+    for (int i = lane; i < p; i += 32) {
+        keys[i] = (unsigned short)i;
+        jdraw[i] = (i >= 1) ? (unsigned short)draw_int(k0, k1, gchain, iter, TAG_PERM, (u32)i, (u32)(i + 1)) : 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = p - 1; i >= 1; --i) { const int j = jdraw[i]; const unsigned short t = keys[i]; keys[i] = keys[j]; keys[j] = t; }
+        for (int c = 0; c < S; ++c) used[keys[c] >> 6] |= 1ull << (keys[c] & 63);
+    }
+    for (int i = lane; i < p * W; i += 32) Mc[i] = 0ull;
+    __syncwarp();
+    for (int i = lane; i < S * W; i += 32) { const int c = i / W, w = i - c * W; Mc[(size_t)keys[c] * W + w] = K[i]; }
+    for (int e = lane; e < ne; e += 32) { E[2 * e] = keys[newe[2 * e]]; E[2 * e + 1] = keys[newe[2 * e + 1]]; }
+    for (int t = lane; t < p; t += 32) {
+        if (bit64(used, t)) continue;
+        int rk = 0;                                   // unused tree nodes below t
+        for (int w = 0; w < (t >> 6); ++w) rk += 64 - __popcll(used[w]);
+        rk += (t & 63) - __popcll(used[t >> 6] & ((1ull << (t & 63)) - 1ull));
+        const int n = S + rk;
+        const int j = (int)draw_int(k0, k1, gchain, iter, TAG_PAD, (u32)t, (u32)n);
+        int target;
+        if (j < S) target = keys[j];
+        else {
+            int r = j - S; target = -1;
+            for (int w = 0; w < W && target < 0; ++w) {
+                u64 x = ~used[w];
+                if (w == W - 1 && (p & 63)) x &= (1ull << (p & 63)) - 1ull;
+                const int cfree = __popcll(x);
+                if (r < cfree) target = w * 64 + select64(x, r); else r -= cfree;
+            }
+        }
+        E[2 * (ne + rk)] = t; E[2 * (ne + rk) + 1] = target;
+    }
+    __syncwarp();
+    __threadfence_block();
+    build_derived(P, chain, lane, s_off, fill);
+}
