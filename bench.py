@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the parallel-MH hot path (BASELINE.json: "MH proposals/sec/box").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one complete sampler run of the named workload: every chain of the batch goes
+through -M iterations with a junction-tree randomisation every -R iterations (parallel-moves
+kernel), starting from the empty graph.  At N = 1 the workload is BASELINE.json configs[1]
+(GGM, AR(1-5) data shape p=50 n=100, -M 10000 -R 100, 1024 chains); with N > 1 every rank runs
+the same number of chains with its own chain ids (weak scaling, chains shard with no data-path
+collective; NCCL only reduces the edge-inclusion tallies and the counters).
+
+Printed by rank 0: ONE JSON line (see the keys below).  `--impl reference` times the CPU oracle
+port of the reference (oracle/pdg_oracle.c, all host threads) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, p, n, M, R, chains per GPU, data seed, delta)
+    "ggm_ar_p50_n100_M10000_R100_c1024": dict(model="ggm", p=50, n=100, M=10000, R=100, chains=1024, seed=50, delta=1.0),
+    "ggm_ar_p500_n1000_M10000_R100_c1024": dict(model="ggm", p=500, n=1000, M=10000, R=100, chains=1024, seed=500, delta=1.0),
+    "ggm_ar_p50_n100_M1000_R100_c1024": dict(model="ggm", p=50, n=100, M=1000, R=100, chains=1024, seed=50, delta=1.0),
+    "loglin_ar_p100_n100000_M10000_R100_c1024": dict(model="loglin", p=100, n=100000, M=10000, R=100, chains=1024, seed=100),
+    "loglin_ar_p15_n1000_M10000_R100_c4096": dict(model="loglin", p=15, n=1000, M=10000, R=100, chains=4096, seed=15),
+}
+DEFAULT_WORKLOAD = "ggm_ar_p50_n100_M10000_R100_c1024"
+METRIC = "mh_proposals_per_sec"
+UNIT = "proposals/s"
+
+
+def build_inputs(w):
+    from paralleldg_b200 import datagen
+    if w["model"] == "ggm":
+        X, adj = datagen.ggm_ar_data(w["p"], w["n"], w["seed"])
+        return dict(X=X)
+    data, levels, adj = datagen.loglin_ar_data(w["p"], w["n"], w["seed"])
+    return dict(data=data, levels=levels)
+
+
+def product_objects(w, inp):
+    from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
+    from paralleldg_b200 import mh_parallel as mh
+    if w["model"] == "ggm":
+        sd = seqdist.GGMJTPosterior()
+        sd.init_model(inp["X"], np.identity(w["p"]), w.get("delta", 1.0), {})
+    else:
+        sd = seqdist.LogLinearJTPosterior()
+        sd.init_model(inp["data"].astype(np.int64), 1.0, [list(range(int(l))) for l in inp["levels"]], {}, {})
+    return sd, mh.get_prior(["mbc", 2.0, 4.0])
+
+
+def oracle_model(w, inp):
+    from oracle import oracle as orc
+    if w["model"] == "ggm":
+        return orc.Model.ggm(inp["X"], None, w.get("delta", 1.0), ("mbc", 2.0, 4.0))
+    return orc.Model.loglin(inp["data"], inp["levels"], 1.0, ("mbc", 2.0, 4.0))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        threading.Thread.__init__(self, daemon=True)
+        self.device = device
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def run_reference_arm(args, wname, w, rank, world):
+    """The reference's CPU path: oracle port (the reference is pure Python and cannot travel to
+    the GPU box), Philox production mode, all host threads, same workload per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    inp = build_inputs(w)
+    m = oracle_model(w, inp)
+    threads = os.cpu_count() or 1
+    chains = w["chains"] * max(1, args.gpus)
+    times, props = [], 0
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        o = orc.run_many(m, orc.KIND_PARALLEL, chains, w["M"], w["R"], seed=1234 + s, n_threads=threads)
+        dt = time.perf_counter() - t
+        assert o["rc"] == 0
+        if s >= args.warmup:
+            times.append(dt)
+            props += int(o["n_prop"].sum())
+    total = float(sum(times))
+    val = props / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "chains_total": chains},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "full workload (%d chains x %d iterations) per step" % (chains, w["M"])},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wname = args.workload
+    w = WORKLOADS[wname]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, wname, w, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from paralleldg_b200 import _native as nat, engine, mh_parallel as mh
+
+    inp = build_inputs(w)
+    sd, sdg = product_objects(w, inp)
+    C, M, R = w["chains"], w["M"], w["R"]
+    chain0 = rank * C
+    seed = 20261019
+    cap = max(M, 64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident arm
+    ctx = engine.make_context(sd, sdg, C, M, seed=seed, chain0=chain0, device=local_rank, rec_cap=cap)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step():
+        ctx.set_cliques(None)
+        ctx.randomize(0)
+        ctx.sample(nat.KIND_PARALLEL, R)
+
+    for _ in range(args.warmup):
+        step()
+        flush.fill_(1)
+    ctx.sync()
+    props_per_step = int(ctx.counts()[0].sum())
+    ctx.enable_timing(True)
+    work0 = ctx.work()
+    launches0 = ctx.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (outside the events)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    clocks.stop_flag = True
+    ctx.sync()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    assert int(ctx.counts()[0].sum()) == props_per_step
+    tm = ctx.timing()
+    work1 = ctx.work()
+    launches = ctx.launch_count() - launches0
+    ctx.enable_timing(False)
+    clocks.join(timeout=2)
+
+    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    n_prop = torch.tensor([float(props_per_step * args.steps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_prop, op=dist.ReduceOp.SUM)
+    value = float(n_prop.item()) / (float(t_dev.item()) * 1e-3)
+
+    # roofline of the dominant kernel (k_mh_run): algorithmic bytes / CUDA-event kernel time
+    wb = work1["bytes"] - work0["bytes"]
+    wf = work1["flops"] - work0["flops"]
+    nsets = work1["sets"] - work0["sets"]
+    sumk = work1["sum_k"] - work0["sum_k"]
+    peak, how = peaks()
+    ach = wb / (tm["ms_run"] * 1e-3) / 1e9 if tm["ms_run"] > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": how, "kernel": "k_mh_run",
+                "kernel_ms_per_step": tm["ms_run"] / max(args.steps, 1),
+                "randomize_ms_per_step": tm["ms_randomize"] / max(args.steps, 1),
+                "kernel_share_of_step": tm["ms_run"] / dev_ms if dev_ms else None,
+                "algorithmic_bytes_per_step": wb / max(args.steps, 1),
+                "fp64_gflops_achieved": wf / (tm["ms_run"] * 1e-3) / 1e9 if tm["ms_run"] > 0 else 0.0,
+                "scored_sets_per_step": nsets / max(args.steps, 1),
+                "mean_set_size": (sumk / nsets) if nsets else None,
+                "note": "latency-bound integer/branch kernel with tiny fp64 blocks; see DESIGN.md"}
+    ctx.close()
+
+    # ------------------------------------------------------------------ end-to-end arm
+    e2e = None
+    if not args.no_e2e:
+        h2d = 0
+        if w["model"] == "ggm":
+            h2d = 2 * w["p"] * w["p"] * 8 + (w["p"] + 1) * 8
+        else:
+            h2d = int(inp["data"].size) + w["p"] * 4
+        d2h = 0
+        e_props = 0
+        for s in range(2):                                    # warm the pooled context
+            mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=seed + s, chain0=chain0, device=local_rank,
+                             rec_cap=cap, want_tallies=True, pooled=True)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            batch = mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=seed + 10 + s, chain0=chain0,
+                                     device=local_rank, rec_cap=cap, want_tallies=True, pooled=True)
+            if world > 1:                                    # the only collective of the path
+                t = torch.from_numpy(batch.tallies).cuda()
+                dist.all_reduce(t)
+                batch.tallies = t.cpu().numpy()
+            e_props += int(batch.n_proposals.sum())
+            d2h = batch.d2h_bytes
+        barrier()
+        e_s = time.perf_counter() - t0
+        et = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+        ep = torch.tensor([float(e_props)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ep, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(ep.item()) / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(et.item()) / max(args.steps, 1),
+               "api": "paralleldg_b200.mh_parallel.sample_chains (host numpy in, host numpy out: logl traces, "
+                      "compacted update records, final states, edge tallies)"}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        m = oracle_model(w, inp)
+        threads = os.cpu_count() or 1
+        # bounded sample: enough chains for ~10-20 s of CPU work, never more than the workload
+        probe_c = max(threads, 8)
+        t = time.perf_counter()
+        o = orc.run_many(m, orc.KIND_PARALLEL, probe_c, min(M, 2000), R, seed=7, n_threads=threads)
+        dt = time.perf_counter() - t
+        rate = o["n_prop"].sum() / dt
+        per_chain = (dt / probe_c) * (M / float(min(M, 2000)))
+        sc = int(min(C, max(probe_c, 12.0 / max(per_chain, 1e-9))))
+        t = time.perf_counter()
+        o = orc.run_many(m, orc.KIND_PARALLEL, sc, M, R, seed=8, n_threads=threads)
+        dt = time.perf_counter() - t
+        cpu = {"value": float(o["n_prop"].sum() / dt), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d of %d chains x %d iterations, oracle/pdg_oracle.c (C port of the reference), %d threads"
+                         % (sc, C, M, threads)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(t_dev.item()) / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": wname, "chains_per_gpu": C, "chains_total": C * world, "iterations": M,
+                           "randomize": R, "kernel": "parallel-moves", "prior": "mbc(2,4)",
+                           "proposals_per_step_per_gpu": props_per_step,
+                           "l2": "flushed between timed steps (256 MB write)"},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

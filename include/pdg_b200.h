@@ -83,6 +83,9 @@ int pdg_abi_version(void);
 int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chain0,
                uint64_t seed, int64_t n_samples, int64_t rec_cap);
 int pdg_destroy(pdg_ctx *ctx);
+/* re-arms a context for another run of the same shape: new Philox key / first chain id, error
+ * flags and counters cleared (lets a host reuse the device allocations across calls) */
+int pdg_set_seed(pdg_ctx *ctx, uint64_t seed, uint32_t chain0);
 const char *pdg_last_error(pdg_ctx *ctx);
 /* the stream every later call is enqueued on (0 = default); a cudaStream_t passed as void* */
 int pdg_set_stream(pdg_ctx *ctx, void *stream);
@@ -146,6 +149,14 @@ int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores)
 /* edge-inclusion tallies (trajectory.py:126-152 + empirical_graph_distribution.py:35-41):
  * tallies[p][p] int64 += sum over chains and MCMC indices >= burnin of the edge indicator */
 int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies);
+
+/* measurement support (bench.py): CUDA-event timing of every MH-kernel and randomisation launch
+ * on the context's stream, and the algorithmic work the MH kernel performed:
+ * work[0] = bytes (8 k^2 per scored complete set), work[1] = 6 x flops
+ * (2k^3 + 3k^2 + 6k per scored set), work[2] = scored sets, work[3] = sum of k */
+int pdg_enable_timing(pdg_ctx *ctx, int on);
+int pdg_get_timing(pdg_ctx *ctx, double *ms_run, double *ms_randomize, int64_t *n_run, int64_t *n_randomize);
+int pdg_get_work(pdg_ctx *ctx, int64_t work[4]);
 
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pdg_launch_count(pdg_ctx *ctx);

@@ -22,6 +22,7 @@ EXPORTS = [
     "pdg_set_cliques", "pdg_randomize", "pdg_init_logl", "pdg_run", "pdg_sample", "pdg_sync",
     "pdg_get_counts", "pdg_get_logl", "pdg_compact_updates", "pdg_get_updates", "pdg_enable_move_log",
     "pdg_get_move_log", "pdg_score_sets", "pdg_edge_tallies", "pdg_launch_count",
+    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed",
 ]
 
 
@@ -74,6 +75,10 @@ def lib():
         "pdg_score_sets": (C.c_int, [vp, vp, i64, vp]),
         "pdg_edge_tallies": (C.c_int, [vp, i64, vp]),
         "pdg_launch_count": (i64, [vp]),
+        "pdg_enable_timing": (C.c_int, [vp, i32]),
+        "pdg_get_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64)]),
+        "pdg_get_work": (C.c_int, [vp, C.POINTER(i64)]),
+        "pdg_set_seed": (C.c_int, [vp, u64, u32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -125,6 +130,9 @@ class Context(object):
         if rc != 0:
             msg = self.L.pdg_last_error(self.h)
             raise NativeError("libpdg_b200 error %d: %s" % (rc, msg.decode() if msg else ""))
+
+    def set_seed(self, seed, chain0=0):
+        self._ck(self.L.pdg_set_seed(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(chain0)))
 
     def set_stream(self, stream_ptr):
         self._ck(self.L.pdg_set_stream(self.h, C.c_void_p(stream_ptr)))
@@ -199,7 +207,7 @@ class Context(object):
         return a, b
 
     def logl(self, out=None):
-        out = np.zeros((self.n_chains, self.n_samples), np.float64) if out is None else out
+        out = np.empty((self.n_chains, self.n_samples), np.float64) if out is None else out
         self._ck(self.L.pdg_get_logl(self.h, _p(out)))
         return out
 
@@ -208,8 +216,8 @@ class Context(object):
         tot = C.c_int64(0)
         off = np.zeros(self.n_chains + 1, np.int64)
         self._ck(self.L.pdg_compact_updates(self.h, C.byref(tot), _p(off)))
-        rec = np.zeros(tot.value, UPDATE_DTYPE)
-        bits = np.zeros((tot.value, 2, self.W), np.uint64)
+        rec = np.empty(tot.value, UPDATE_DTYPE)
+        bits = np.empty((tot.value, 2, self.W), np.uint64)
         self._ck(self.L.pdg_get_updates(self.h, _p(rec), _p(bits)))
         return off, rec, bits
 
@@ -235,6 +243,19 @@ class Context(object):
         out = np.zeros((self.p, self.p), np.int64)
         self._ck(self.L.pdg_edge_tallies(self.h, int(burnin), _p(out)))
         return out
+
+    def enable_timing(self, on=True):
+        self._ck(self.L.pdg_enable_timing(self.h, 1 if on else 0))
+
+    def timing(self):
+        a, b, na, nb = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.pdg_get_timing(self.h, C.byref(a), C.byref(b), C.byref(na), C.byref(nb)))
+        return dict(ms_run=a.value, ms_randomize=b.value, n_run=na.value, n_randomize=nb.value)
+
+    def work(self):
+        w = (C.c_int64 * 4)()
+        self._ck(self.L.pdg_get_work(self.h, w))
+        return dict(bytes=int(w[0]), flops=int(w[1]) / 6.0, sets=int(w[2]), sum_k=int(w[3]))
 
     def launch_count(self):
         return int(self.L.pdg_launch_count(self.h))

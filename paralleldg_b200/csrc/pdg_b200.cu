@@ -11,6 +11,7 @@
 
 #include "pdg_run.cuh"
 #include "pdg_randomize.cuh"
+#include "pdg_tally.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // logl[0] (mh_parallel.py:59-60 / :217-218): clique scores in tree-node order minus
@@ -179,7 +180,24 @@ struct pdg_ctx {
     // replay staging
     std::vector<void *> replay_tmp;
     int nwarps = 4;
+    // CUDA-event timing of the MH and randomisation launches
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_run, ev_rand;
 };
+
+static void time_begin(pdg_ctx *ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &v)
+{
+    if (!ctx->timing) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+    v.push_back(std::make_pair(a, b));
+}
+static void time_end(pdg_ctx *ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &v)
+{
+    if (!ctx->timing) return;
+    cudaEventRecord(v.back().second, ctx->stream);
+}
 
 static int fail(pdg_ctx *c, int code, const std::string &msg)
 {
@@ -216,7 +234,9 @@ static int launch_run(pdg_ctx *ctx, long long b, long long e, const PdgReplayDev
     const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, ctx->nwarps);
     int rc;
     if ((rc = set_smem(ctx, k_mh_run<MODEL, KIND>, L.total))) return rc;
+    time_begin(ctx, ctx->ev_run);
     k_mh_run<MODEL, KIND><<<(unsigned)ctx->P.n_chains, NT, L.total, ctx->stream>>>(ctx->P, b, e, R);
+    time_end(ctx, ctx->ev_run);
     ctx->launches++;
     CK(cudaGetLastError());
     return PDG_OK;
@@ -268,6 +288,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     if (device < 0 || device >= ndev) return PDG_E_ARG;
     pdg_ctx *ctx = new pdg_ctx();
     ctx->device = device;
+    if (const char *nwv = getenv("PDG_NWARPS")) { const int v = atoi(nwv); if (v >= 1 && v <= 4) ctx->nwarps = v; }
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PDG_E_CUDA; }
     PdgParams &P = ctx->P;
     memset(&P, 0, sizeof(P));
@@ -287,6 +308,8 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     TRY(dalloc(ctx, &P.kcount, C));
     TRY(dalloc(ctx, &P.nrec, C));
     TRY(dalloc(ctx, &P.err, C));
+    TRY(dalloc(ctx, &P.work, C * 4));
+    TRY(dalloc(ctx, &P.G0, C * pw));
     TRY(dalloc(ctx, &P.rec, C * (size_t)rec_cap));
     TRY(dalloc(ctx, &P.rec_bits, C * (size_t)rec_cap * 2 * P.W));
     TRY(dalloc(ctx, &ctx->Z.adj, C * pw));
@@ -298,6 +321,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     if (P.kbig > 32) TRY(dalloc(ctx, &P.big, C * ctx->nwarps * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2)));
     else { P.kbig = 0; P.big = nullptr; }
     TRY(cudaMemset(P.err, 0, C * sizeof(int)));
+    TRY(cudaMemset(P.work, 0, C * 4 * sizeof(unsigned long long)));
     TRY(cudaMemset(P.kcount, 0, C * sizeof(long long)));
     TRY(cudaMemset(P.nrec, 0, C * sizeof(long long)));
     TRY(cudaMemset(P.logl, 0, C * (size_t)n_samples * sizeof(double)));
@@ -326,6 +350,21 @@ int pdg_destroy(pdg_ctx *ctx)
     if (ctx->d_packed_bits) cudaFree(ctx->d_packed_bits);
     if (ctx->P.ml_dlik) { cudaFree(ctx->P.ml_dlik); cudaFree(ctx->P.ml_dprior); cudaFree(ctx->P.ml_logq); cudaFree(ctx->P.ml_u); cudaFree(ctx->P.ml_acc); cudaFree(ctx->P.ml_U); }
     delete ctx;
+    return PDG_OK;
+}
+
+int pdg_set_seed(pdg_ctx *ctx, uint64_t seed, uint32_t chain0)
+{
+    if (!ctx) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PdgParams &P = ctx->P;
+    P.seed_lo = (u32)seed; P.seed_hi = (u32)(seed >> 32); P.chain0 = chain0;
+    const size_t C = (size_t)P.n_chains;
+    CK(cudaMemsetAsync(P.err, 0, C * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(P.kcount, 0, C * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(P.nrec, 0, C * sizeof(long long), ctx->stream));
+    ctx->packed_total = -1;
+    ctx->state_set = false;
     return PDG_OK;
 }
 
@@ -466,7 +505,9 @@ int pdg_randomize(pdg_ctx *ctx, uint32_t iter)
     CK(cudaSetDevice(ctx->device));
     const RandSmem L = rand_smem_layout(ctx->P.p, ctx->P.W);
     if (L.total > 48 * 1024) CK(cudaFuncSetAttribute(k_randomize, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    time_begin(ctx, ctx->ev_rand);
     k_randomize<<<(unsigned)ctx->P.n_chains, 32, L.total, ctx->stream>>>(ctx->P, ctx->Z, iter);
+    time_end(ctx, ctx->ev_rand);
     ctx->launches++;
     CK(cudaGetLastError());
     return PDG_OK;
@@ -487,6 +528,9 @@ int pdg_init_logl(pdg_ctx *ctx, int kind)
         if ((rc = set_smem(ctx, k_init_logl<PDG_MODEL_UNIFORM>, L.total))) return rc;
         k_init_logl<PDG_MODEL_UNIFORM><<<(unsigned)ctx->P.n_chains, NT, L.total, ctx->stream>>>(ctx->P, kind);
     }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    k_snapshot_graph<<<(unsigned)ctx->P.n_chains, 32, 0, ctx->stream>>>(ctx->P);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->packed_total = -1;
@@ -689,8 +733,62 @@ int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores)
 
 int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies)
 {
+    if (!ctx || !tallies || burnin < 0) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PdgParams &P = ctx->P;
+    const size_t pp = (size_t)P.p * P.p;
+    int *since = nullptr; unsigned long long *d_t = nullptr;
+    CK(cudaMalloc((void **)&since, (size_t)P.n_chains * pp * sizeof(int)));
+    CK(cudaMalloc((void **)&d_t, pp * 8));
+    CK(cudaMemsetAsync(d_t, 0, pp * 8, ctx->stream));
+    k_edge_tallies<<<(unsigned)P.n_chains, 32, 0, ctx->stream>>>(P, since, burnin, d_t);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<long long> h(pp);
+    CK(cudaMemcpyAsync(h.data(), d_t, pp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(since); cudaFree(d_t);
+    for (int a = 0; a < P.p; ++a)
+        for (int b = a + 1; b < P.p; ++b) h[(size_t)b * P.p + a] = h[(size_t)a * P.p + b];
+    CK(cudaMemcpy(tallies, h.data(), pp * 8, cudaMemcpyDefault));
+    return PDG_OK;
+}
+
+int pdg_enable_timing(pdg_ctx *ctx, int on)
+{
     if (!ctx) return PDG_E_ARG;
-    return fail(ctx, PDG_E_STATE, "edge tallies not built in this revision");
+    ctx->timing = on != 0;
+    for (auto &e : ctx->ev_run) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : ctx->ev_rand) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    ctx->ev_run.clear(); ctx->ev_rand.clear();
+    return PDG_OK;
+}
+
+int pdg_get_timing(pdg_ctx *ctx, double *ms_run, double *ms_randomize, int64_t *n_run, int64_t *n_randomize)
+{
+    if (!ctx) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double a = 0.0, b = 0.0;
+    for (auto &e : ctx->ev_run) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e.first, e.second)); a += ms; }
+    for (auto &e : ctx->ev_rand) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e.first, e.second)); b += ms; }
+    if (ms_run) *ms_run = a;
+    if (ms_randomize) *ms_randomize = b;
+    if (n_run) *n_run = (int64_t)ctx->ev_run.size();
+    if (n_randomize) *n_randomize = (int64_t)ctx->ev_rand.size();
+    return PDG_OK;
+}
+
+int pdg_get_work(pdg_ctx *ctx, int64_t work[4])
+{
+    if (!ctx || !work) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<unsigned long long> h((size_t)ctx->P.n_chains * 4);
+    CK(cudaMemcpy(h.data(), ctx->P.work, h.size() * 8, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 4; ++q) work[q] = 0;
+    for (size_t c = 0; c < (size_t)ctx->P.n_chains; ++c) for (int q = 0; q < 4; ++q) work[q] += (int64_t)h[c * 4 + q];
+    return PDG_OK;
 }
 
 }  // extern "C"

@@ -31,6 +31,8 @@ struct PdgParams {
     u64 *rec_bits;              // [chain][rec_cap][2][W]
     long long rec_cap;
     int *err;                   // [chain]
+    unsigned long long *work;   // [chain][4]: bytes, 6*flops, scored sets, sum k
+    u64 *G0;                    // [chain][p][W] graph adjacency at MCMC index 0 (for edge tallies)
     // per-proposal diagnostics (optional)
     long long mvlog_cap;
     double *ml_dlik, *ml_dprior, *ml_logq, *ml_u;

@@ -8,7 +8,7 @@
 // shared-memory carve-up, identical on host and device
 struct RunSmem {
     int off_tri, off_idx, off_delta, off_dl, off_dp, off_u, off_sub, off_leaf, off_bnd, off_partner,
-        off_mvU, off_mvUadj, off_acc, off_csr_off, off_csr_adj, total;
+        off_mvU, off_mvUadj, off_acc, off_csr_off, off_csr_adj, off_work, total;
 };
 
 __host__ __device__ inline RunSmem run_smem_layout(int p, int W, int nwarps)
@@ -17,6 +17,7 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, int nwarps)
     int o = 0;
     const int np32 = ((p + 31) / 32) + 1;
     s.off_tri = o;      o += nwarps * 528 * 8;
+    s.off_work = o;     o += nwarps * 4 * 8;
     s.off_delta = o;    o += p * 8;
     s.off_dl = o;       o += p * 8;
     s.off_dp = o;       o += p * 8;
@@ -85,6 +86,8 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
     double logl_prev = P.logl[(size_t)chain * P.n_samples + it_begin - 1];
     int errflag = 0;
     const int npass = (p + NT - 1) / NT;
+    unsigned long long *s_work = (unsigned long long *)(smem + L.off_work) + warp * 4;
+    if (lane < 4) s_work[lane] = 0ull;
 
     for (long long it = it_begin; it < it_end; ++it) {
         // ---- draws (mh_parallel.py:230-231) -------------------------------------------
@@ -228,6 +231,18 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
             }
             if (lane == 0) {
                 const bool adj = Ua >= 0;
+                if (MODEL != PDG_MODEL_UNIFORM) {
+                    // algorithmic work of this proposal: the complete sets the reference scores
+                    const int ksz[4] = {kb, ks, kb + 1, adj ? ks + 1 : 0};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const unsigned long long kk_ = (unsigned long long)ksz[q];
+                        if (!kk_) continue;
+                        s_work[0] += 8ull * kk_ * kk_ * (P.dmode == 2 ? 2ull : 1ull);
+                        s_work[1] += (2ull * kk_ * kk_ * kk_ + 3ull * kk_ * kk_ + 6ull * kk_) * (P.dmode == 2 ? 2ull : 1ull);
+                        s_work[2] += 1ull; s_work[3] += kk_;
+                    }
+                }
                 double log_p2, log_p1, log_g2, log_g1;
                 if (mtype == 0) {
                     const int cC = kb, cS = ks, cCn = kb + 1, cSn = adj ? ks + 1 : 0;
@@ -299,5 +314,7 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
         __syncthreads();
     }
     if (tid == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
+    __syncwarp();
+    if (lane < 4 && s_work[2]) atomicAdd(&P.work[chain * 4 + lane], s_work[lane]);
     if (errflag) atomicOr(&P.err[chain], errflag);
 }

@@ -34,8 +34,20 @@ def configure_model(ctx, sd):
                         "LogLinearJTPosterior, UniformJTDistribution); there is no CPU fallback" % (sd,))
 
 
-def make_context(sd, sd_graph, n_chains, n_samples, seed=0, chain0=0, device=0, rec_cap=None):
-    ctx = nat.Context(sd.p, n_chains, n_samples, seed=seed, chain0=chain0, device=device, rec_cap=rec_cap)
+_POOL = {}
+
+
+def make_context(sd, sd_graph, n_chains, n_samples, seed=0, chain0=0, device=0, rec_cap=None, pooled=False):
+    """New (or, with pooled=True, recycled) native context with prior and model uploaded.  A
+    pooled context keeps its device allocations between calls of the same shape; give it back
+    with release_context()."""
+    key = (int(device), int(sd.p), int(n_chains), int(n_samples), None if rec_cap is None else int(rec_cap))
+    ctx = _POOL.pop(key, None) if pooled else None
+    if ctx is not None:
+        ctx.set_seed(seed, chain0)
+    else:
+        ctx = nat.Context(sd.p, n_chains, n_samples, seed=seed, chain0=chain0, device=device, rec_cap=rec_cap)
+    ctx._pool_key = key if pooled else None
     try:
         import torch
         if torch.cuda.is_available():
@@ -46,6 +58,14 @@ def make_context(sd, sd_graph, n_chains, n_samples, seed=0, chain0=0, device=0, 
     ctx.set_prior(k, a, b)
     configure_model(ctx, sd)
     return ctx
+
+
+def release_context(ctx):
+    key = getattr(ctx, "_pool_key", None)
+    if key is None or key in _POOL:
+        ctx.close()
+    else:
+        _POOL[key] = ctx
 
 
 def set_bits(sets, W):
