@@ -101,10 +101,11 @@ int pdg_set_model_uniform(pdg_ctx *ctx);
 int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, double delta,
                       const void *gconst);
 /* replaces: LogLinearJTPosterior.init_model (seqdist:239-252).  data: column-major level codes
- * [p][nrows] uint8; levels[p]; lgtab (nullable): [n_ktab][nrows+1] fp64 with
- * lgtab[j][c] = lgamma(c + alpha_j) - lgamma(alpha_j) for the j-th distinct cell count
- * ktab[j] = prod of levels over a set (dirichlet.py:76-83), alpha_j = alphatab[j]
- * (loglin:52-55); when NULL the device lgamma is used. */
+ * [p][nrows] uint8; levels[p]; optional lgamma tables for n_ktab distinct cell counts
+ * ktab[j] = prod of levels over a set (fp64): alphatab[j] = the per-cell pseudo count of such a
+ * set (loglin:52-55), lgtab[j][c] = lgamma(c + alpha_j) - lgamma(alpha_j) for c = 0..nrows
+ * (dirichlet.py:76-83) and lgtab[j][nrows+1] = lgamma(K alpha_j + nrows) - lgamma(K alpha_j)
+ * (row stride nrows + 2).  Sets whose cell count is not in ktab use the device lgamma. */
 int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int64_t nrows,
                          double cell_alpha, int n_ktab, const void *ktab, const void *alphatab,
                          const void *lgtab);
@@ -151,12 +152,13 @@ int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores)
 int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies);
 
 /* measurement support (bench.py): CUDA-event timing of every MH-kernel and randomisation launch
- * on the context's stream, and the algorithmic work the MH kernel performed:
- * work[0] = bytes (8 k^2 per scored complete set), work[1] = 6 x flops
- * (2k^3 + 3k^2 + 6k per scored set), work[2] = scored sets, work[3] = sum of k */
+ * on the context's stream, and the algorithmic work the MH kernel performed (SURVEY.md 8(d)):
+ * for the complete sets actually EVALUATED (memo misses): work[0] = bytes (GGM 8 k^2, log-linear
+ * n k per set), work[1] = 6 x flops (GGM 2k^3 + 3k^2 + 6k per set), work[2] = sets, work[3] = sum
+ * of k; for the sets REQUESTED by proposals (hits + misses): work[4] = sets, work[5] = sum of k */
 int pdg_enable_timing(pdg_ctx *ctx, int on);
 int pdg_get_timing(pdg_ctx *ctx, double *ms_run, double *ms_randomize, int64_t *n_run, int64_t *n_randomize);
-int pdg_get_work(pdg_ctx *ctx, int64_t work[4]);
+int pdg_get_work(pdg_ctx *ctx, int64_t work[8]);
 
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pdg_launch_count(pdg_ctx *ctx);

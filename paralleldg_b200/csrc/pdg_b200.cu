@@ -16,75 +16,92 @@
 // ---------------------------------------------------------------------------------------------
 // logl[0] (mh_parallel.py:59-60 / :217-218): clique scores in tree-node order minus
 // nu_s * score(s) over the DISTINCT non-empty separators (first occurrence in edge order), plus
-// log_prior over cliques and distinct separators (seqdist:44-52).
-struct InitSmem { int off_tri, off_idx, off_buf, off_sc, off_ss, off_cs, off_ssz, off_nu, off_first, total; };
-__host__ __device__ inline InitSmem init_smem_layout(int p, int W, int nw)
+// log_prior over cliques and distinct separators (seqdist:44-52).  One warp per chain.
+struct InitSmem { int off_tri, off_lidx, off_idx, off_sc, off_ss, off_cs, off_ssz, off_nu, off_first, total; };
+__host__ __device__ inline InitSmem init_smem_layout(int p, int W)
 {
     InitSmem s; int o = 0;
-    s.off_tri = o; o += nw * 528 * 8;
+    const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
+    s.off_tri = o; o += 528 * 8;
+    s.off_lidx = o;
     s.off_sc = o; o += p * 8;
     s.off_ss = o; o += p * 8;
-    s.off_buf = o; o += nw * W * 8;
-    s.off_idx = o; o += nw * ((((p + 1) * 2 + 15) / 16) * 16);
-    s.off_cs = o; o += ((p * 2 + 15) / 16) * 16;
-    s.off_ssz = o; o += ((p * 2 + 15) / 16) * 16;
-    s.off_nu = o; o += ((p * 2 + 15) / 16) * 16;
-    s.off_first = o; o += ((p + 15) / 16) * 16;
+    s.off_idx = o; o += a2;
+    s.off_cs = o; o += a2;
+    s.off_ssz = o; o += a2;
+    s.off_nu = o; o += a2;
+    s.off_first = o; o += (p + 15) / 16 * 16;
     s.total = o;
     return s;
 }
 
-template <int MODEL>
-__global__ void __launch_bounds__(128) k_init_logl(PdgParams P, int kind)
+// one set, same value on every lane: lane 0 carries the key through warp_scores so that logl[0]
+// uses exactly the score function of the sampler
+template <int MODEL, int WMAX>
+__device__ __forceinline__ int set_score_any(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
+                                             const u64 (&X)[WMAX], int lane, double &sc)
+{
+    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    double v = 0.0;
+    const int e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, lane == 0, v, wk);
+    sc = __shfl_sync(PDG_FULL, v, 0);
+    return __reduce_or_sync(PDG_FULL, (unsigned)e);
+}
+
+template <int MODEL, int WMAX>
+__global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int p = P.p, W = P.W;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int p = P.p, W = P.W, lane = threadIdx.x;
     const long long chain = blockIdx.x;
-    const InitSmem L = init_smem_layout(p, W, nw);
+    const InitSmem L = init_smem_layout(p, W);
     double *s_sc = (double *)(smem + L.off_sc), *s_ss = (double *)(smem + L.off_ss);
     unsigned short *s_cs = (unsigned short *)(smem + L.off_cs), *s_ssz = (unsigned short *)(smem + L.off_ssz);
     unsigned short *s_nu = (unsigned short *)(smem + L.off_nu);
     unsigned char *s_first = smem + L.off_first;
-    u64 *buf = (u64 *)(smem + L.off_buf) + warp * W;
     WarpScratch ws;
-    ws.tri32 = (double *)(smem + L.off_tri) + warp * 528;
-    ws.idx = (short *)(smem + L.off_idx) + warp * ((((p + 1) * 2 + 15) / 16) * 8);
+    ws.tri32 = (double *)(smem + L.off_tri);
+    ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;
-    ws.big = P.big ? P.big + ((size_t)chain * nw + warp) * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    const int slot = (int)chain;
+    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    LaneScratch ls;
+    ls.unused = 0;
     const u64 *Mc = P.M + (size_t)chain * p * W;
     const int *E = P.edges + (size_t)chain * 2 * (p - 1);
     int errflag = 0;
-    for (int t = warp; t < p; t += nw) {
-        const u64 *row = Mc + (size_t)t * W;
+    for (int t = 0; t < p; ++t) {
+        u64 X[WMAX];
+        load_row<WMAX>(X, Mc + (size_t)t * W, W);
         int cs = 0;
-        for (int w = 0; w < W; ++w) cs += __popcll(row[w]);
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) cs += __popcll(X[w]);
         double sc = 0.0;
-        if (MODEL == PDG_MODEL_GGM && cs > 0) { const int e = ggm_set_score(P, ws, row, lane, sc); if (e) errflag |= e; }
+        if (MODEL != PDG_MODEL_UNIFORM && cs > 0) errflag |= set_score_any<MODEL, WMAX>(P, ws, ls, slot, X, lane, sc);
         if (lane == 0) { s_sc[t] = sc; s_cs[t] = (unsigned short)cs; }
     }
-    for (int e = warp; e < p - 1; e += nw) {
+    for (int e = 0; e < p - 1; ++e) {
         const int a = E[2 * e], b = E[2 * e + 1];
-        if (lane < W) buf[lane] = Mc[(size_t)a * W + lane] & Mc[(size_t)b * W + lane];
-        __syncwarp();
+        u64 X[WMAX];
         int sz = 0;
-        for (int w = 0; w < W; ++w) sz += __popcll(buf[w]);
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) { X[w] = (w < W) ? (Mc[(size_t)a * W + w] & Mc[(size_t)b * W + w]) : 0ull; sz += __popcll(X[w]); }
         int nu = 0; bool first = true;
         for (int e2 = lane; e2 < p - 1; e2 += 32) {
             const int a2 = E[2 * e2], b2 = E[2 * e2 + 1];
             bool same = true;
-            for (int w = 0; w < W; ++w) same = same && ((Mc[(size_t)a2 * W + w] & Mc[(size_t)b2 * W + w]) == buf[w]);
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w) if (w < W) same = same && ((Mc[(size_t)a2 * W + w] & Mc[(size_t)b2 * W + w]) == X[w]);
             if (same) { ++nu; if (e2 < e) first = false; }
         }
         nu = warp_sum_i(nu);
         first = __all_sync(PDG_FULL, first);
         double sc = 0.0;
-        if (MODEL == PDG_MODEL_GGM && first && sz > 0) { const int er = ggm_set_score(P, ws, buf, lane, sc); if (er) errflag |= er; }
+        if (MODEL != PDG_MODEL_UNIFORM && first && sz > 0) errflag |= set_score_any<MODEL, WMAX>(P, ws, ls, slot, X, lane, sc);
         if (lane == 0) { s_ss[e] = sc; s_ssz[e] = (unsigned short)sz; s_nu[e] = (unsigned short)nu; s_first[e] = first ? 1 : 0; }
-        __syncwarp();
     }
-    __syncthreads();
-    if (tid == 0) {
+    __syncwarp();
+    if (lane == 0) {
         double cl = 0.0, lclq = 0.0;
         for (int t = 0; t < p; ++t) {
             if (s_cs[t] == 0) continue;
@@ -113,23 +130,45 @@ __global__ void __launch_bounds__(128) k_init_logl(PdgParams P, int kind)
     if (errflag) atomicOr(&P.err[chain], errflag);
 }
 
-// batch scorer: one warp per complete set (sd.log_likelihood_partial([c], {}))
-template <int MODEL>
-__global__ void __launch_bounds__(128) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err)
+// batch scorer (sd.log_likelihood_partial([c], {})): every LANE takes one complete set, so a
+// warp scores 32 sets per pass through the same routine the sampler uses (warp_scores); sets
+// above PDG_KT vertices and log-linear sets are resolved cooperatively.  grid <= n_chains because
+// the per-warp scratch (large triangles, cell tables) is sized per chain.
+template <int MODEL, int WMAX>
+__global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int p = P.p, W = P.W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int W = P.W, lane = threadIdx.x;
     WarpScratch ws;
-    ws.tri32 = (double *)smem + warp * 528;
-    ws.idx = (short *)(smem + nw * 528 * 8) + warp * ((((p + 1) * 2 + 15) / 16) * 8);
+    LaneScratch ls;
+    ws.tri32 = (double *)smem;
+    ls.unused = 0;
+    ws.idx = (short *)(smem + 528 * 8);
     ws.kbig = P.kbig;
-    ws.big = P.big ? P.big + ((size_t)blockIdx.x * nw + warp) * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
-    for (long long s = (long long)blockIdx.x * nw + warp; s < n_sets; s += (long long)gridDim.x * nw) {
+    const int slot = blockIdx.x;
+    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    for (long long s0 = (long long)blockIdx.x * 32; s0 < n_sets; s0 += (long long)gridDim.x * 32) {
+        const long long s = s0 + lane;
+        u64 X[WMAX];
+        int k = 0;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) { X[w] = (s < n_sets && w < W) ? bits[(size_t)s * W + w] : 0ull; k += __popcll(X[w]); }
         double sc = 0.0;
-        if (MODEL == PDG_MODEL_GGM) { const int e = ggm_set_score(P, ws, bits + (size_t)s * W, lane, sc); if (e && lane == 0) atomicOr(err, e); }
-        if (lane == 0) out[s] = sc;
+        int e = 0;
+        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, s < n_sets && k > 0, sc, wk);
+        if (e) atomicOr(err, e);
+        if (s < n_sets) out[s] = sc;
         __syncwarp();
+    }
+}
+
+__global__ void k_memo_clear(MemoTable T)
+{
+    const size_t n = (size_t)T.mask + 1, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0; i < n; i += st) {
+        if (T.W == 1) T.kv[i] = make_ulonglong2(0ull, MEMO_SENT);
+        else { T.tag[i] = 0ull; T.val[i] = MEMO_SENT; }
     }
 }
 
@@ -172,6 +211,11 @@ struct pdg_ctx {
     std::vector<void *> owned;
     // model buffers (replaced on re-set)
     double *d_A = nullptr, *d_D = nullptr, *d_logD = nullptr, *d_gconst = nullptr;
+    std::vector<void *> model_owned;      // log-linear buffers, freed on re-set / destroy
+    int wmax = 1;                         // compile-time word count the kernels are dispatched on
+    int wpc = 1;                          // warps (= chains) per CTA of the MH kernel
+    bool smem_state = false;
+    int memo_bits = 20;
     // compaction
     long long *d_offsets = nullptr;
     pdg_update *d_packed = nullptr;
@@ -179,7 +223,6 @@ struct pdg_ctx {
     long long packed_total = -1, packed_cap = 0;
     // replay staging
     std::vector<void *> replay_tmp;
-    int nwarps = 4;
     // CUDA-event timing of the MH and randomisation launches
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_run, ev_rand;
@@ -227,30 +270,101 @@ static int set_smem(pdg_ctx *ctx, F f, int bytes)
     return PDG_OK;
 }
 
-template <int MODEL, int KIND>
-static int launch_run(pdg_ctx *ctx, long long b, long long e, const PdgReplayDev &R)
+template <int MODEL, int WMAX, bool SS>
+static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R)
 {
-    const int NT = ctx->nwarps * 32;
-    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, ctx->nwarps);
+    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS);
+    const int wpc = ctx->wpc, sm = L.total * wpc;
     int rc;
-    if ((rc = set_smem(ctx, k_mh_run<MODEL, KIND>, L.total))) return rc;
+    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS>, sm))) return rc;
+    const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
     time_begin(ctx, ctx->ev_run);
-    k_mh_run<MODEL, KIND><<<(unsigned)ctx->P.n_chains, NT, L.total, ctx->stream>>>(ctx->P, b, e, R);
+    const int lockstep = (wpc > 1 && (long long)grid * wpc == ctx->P.n_chains && !getenv("PDG_NO_LOCKSTEP")) ? 1 : 0;
+    k_mh_run<MODEL, WMAX, SS><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep);
     time_end(ctx, ctx->ev_run);
     ctx->launches++;
     CK(cudaGetLastError());
     return PDG_OK;
 }
 
+template <int MODEL, int WMAX>
+static int launch_run_w(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R)
+{
+    if (ctx->smem_state) return launch_run_t<MODEL, WMAX, true>(ctx, kind, b, e, R);
+    return launch_run_t<MODEL, WMAX, false>(ctx, kind, b, e, R);
+}
+
+template <int MODEL>
+static int launch_run_m(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R)
+{
+    switch (ctx->wmax) {
+    case 1: return launch_run_w<MODEL, 1>(ctx, kind, b, e, R);
+    case 2: return launch_run_w<MODEL, 2>(ctx, kind, b, e, R);
+    case 4: return launch_run_w<MODEL, 4>(ctx, kind, b, e, R);
+    default: return launch_run_w<MODEL, 8>(ctx, kind, b, e, R);
+    }
+}
+
 static int run_dispatch(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R)
 {
-    const int m = ctx->P.model;
-    if (kind == PDG_KIND_PARALLEL) {
-        if (m == PDG_MODEL_GGM) return launch_run<PDG_MODEL_GGM, PDG_KIND_PARALLEL>(ctx, b, e, R);
-        return launch_run<PDG_MODEL_UNIFORM, PDG_KIND_PARALLEL>(ctx, b, e, R);
+    switch (ctx->P.model) {
+    case PDG_MODEL_GGM: return launch_run_m<PDG_MODEL_GGM>(ctx, kind, b, e, R);
+    case PDG_MODEL_LOGLIN: return launch_run_m<PDG_MODEL_LOGLIN>(ctx, kind, b, e, R);
+    default: return launch_run_m<PDG_MODEL_UNIFORM>(ctx, kind, b, e, R);
     }
-    if (m == PDG_MODEL_GGM) return launch_run<PDG_MODEL_GGM, PDG_KIND_SINGLE>(ctx, b, e, R);
-    return launch_run<PDG_MODEL_UNIFORM, PDG_KIND_SINGLE>(ctx, b, e, R);
+}
+
+template <int MODEL, int WMAX>
+static int launch_init_t(pdg_ctx *ctx, int kind)
+{
+    const InitSmem L = init_smem_layout(ctx->P.p, ctx->P.W);
+    int rc;
+    if ((rc = set_smem(ctx, k_init_logl<MODEL, WMAX>, L.total))) return rc;
+    k_init_logl<MODEL, WMAX><<<(unsigned)ctx->P.n_chains, 32, L.total, ctx->stream>>>(ctx->P, kind);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PDG_OK;
+}
+
+template <int MODEL>
+static int launch_init_m(pdg_ctx *ctx, int kind)
+{
+    switch (ctx->wmax) {
+    case 1: return launch_init_t<MODEL, 1>(ctx, kind);
+    case 2: return launch_init_t<MODEL, 2>(ctx, kind);
+    case 4: return launch_init_t<MODEL, 4>(ctx, kind);
+    default: return launch_init_t<MODEL, 8>(ctx, kind);
+    }
+}
+
+template <int MODEL, int WMAX>
+static int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
+{
+    long long grid = n_sets < ctx->P.n_chains ? n_sets : ctx->P.n_chains;
+    const int sm = 528 * 8 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PDG_OK;
+}
+
+template <int MODEL>
+static int launch_score_m(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
+{
+    switch (ctx->wmax) {
+    case 1: return launch_score_t<MODEL, 1>(ctx, d_bits, n_sets, d_out, d_err);
+    case 2: return launch_score_t<MODEL, 2>(ctx, d_bits, n_sets, d_out, d_err);
+    case 4: return launch_score_t<MODEL, 4>(ctx, d_bits, n_sets, d_out, d_err);
+    default: return launch_score_t<MODEL, 8>(ctx, d_bits, n_sets, d_out, d_err);
+    }
+}
+
+static int memo_clear(pdg_ctx *ctx)
+{
+    k_memo_clear<<<296, 256, 0, ctx->stream>>>(ctx->P.memo);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PDG_OK;
 }
 
 template <typename T>
@@ -282,13 +396,14 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
 {
     if (!out) return PDG_E_ARG;
     *out = nullptr;
-    if (p < 2 || p > 4096 || n_chains < 1 || n_samples < 1 || rec_cap < 0) return PDG_E_ARG;
+    if (p < 2 || p > 64 * PDG_WMAX_LIMIT || n_chains < 1 || n_samples < 1 || rec_cap < 0) return PDG_E_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PDG_E_CUDA;   // no CPU fallback
     if (device < 0 || device >= ndev) return PDG_E_ARG;
     pdg_ctx *ctx = new pdg_ctx();
     ctx->device = device;
-    if (const char *nwv = getenv("PDG_NWARPS")) { const int v = atoi(nwv); if (v >= 1 && v <= 4) ctx->nwarps = v; }
+    if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) ctx->wpc = x; }
+    if (const char *v = getenv("PDG_MEMO_BITS")) { const int x = atoi(v); if (x >= 8 && x <= 26) ctx->memo_bits = x; }
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PDG_E_CUDA; }
     PdgParams &P = ctx->P;
     memset(&P, 0, sizeof(P));
@@ -308,7 +423,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     TRY(dalloc(ctx, &P.kcount, C));
     TRY(dalloc(ctx, &P.nrec, C));
     TRY(dalloc(ctx, &P.err, C));
-    TRY(dalloc(ctx, &P.work, C * 4));
+    TRY(dalloc(ctx, &P.work, C * 8));
     TRY(dalloc(ctx, &P.G0, C * pw));
     TRY(dalloc(ctx, &P.rec, C * (size_t)rec_cap));
     TRY(dalloc(ctx, &P.rec_bits, C * (size_t)rec_cap * 2 * P.W));
@@ -318,10 +433,22 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     TRY(dalloc(ctx, &ctx->d_offsets, C + 1));
     // scratch for cliques above the 32-row shared-memory triangle
     P.kbig = p + 1 < 256 ? p + 1 : 256;
-    if (P.kbig > 32) TRY(dalloc(ctx, &P.big, C * ctx->nwarps * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2)));
+    if (P.kbig > 32) TRY(dalloc(ctx, &P.big, C * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2)));
     else { P.kbig = 0; P.big = nullptr; }
     TRY(cudaMemset(P.err, 0, C * sizeof(int)));
-    TRY(cudaMemset(P.work, 0, C * 4 * sizeof(unsigned long long)));
+    TRY(cudaMemset(P.work, 0, C * 8 * sizeof(unsigned long long)));
+    {
+        const int W = P.W;
+        ctx->wmax = W <= 1 ? 1 : W <= 2 ? 2 : W <= 4 ? 4 : 8;
+        ctx->smem_state = (size_t)p * W * 16 <= 8192;
+        MemoTable &T = P.memo;
+        T.W = (ctx->wmax == 1) ? 1 : W;
+        T.mask = (1u << ctx->memo_bits) - 1u;
+        const size_t slots = (size_t)1 << ctx->memo_bits;
+        T.kv = nullptr; T.tag = nullptr; T.keyw = nullptr; T.val = nullptr;
+        if (ctx->wmax == 1) { TRY(dalloc(ctx, &T.kv, slots)); }
+        else { TRY(dalloc(ctx, &T.tag, slots)); TRY(dalloc(ctx, &T.val, slots)); TRY(dalloc(ctx, &T.keyw, slots * W)); }
+    }
     TRY(cudaMemset(P.kcount, 0, C * sizeof(long long)));
     TRY(cudaMemset(P.nrec, 0, C * sizeof(long long)));
     TRY(cudaMemset(P.logl, 0, C * (size_t)n_samples * sizeof(double)));
@@ -346,6 +473,7 @@ int pdg_destroy(pdg_ctx *ctx)
     if (ctx->d_D) cudaFree(ctx->d_D);
     if (ctx->d_logD) cudaFree(ctx->d_logD);
     if (ctx->d_gconst) cudaFree(ctx->d_gconst);
+    for (void *v : ctx->model_owned) cudaFree(v);
     if (ctx->d_packed) cudaFree(ctx->d_packed);
     if (ctx->d_packed_bits) cudaFree(ctx->d_packed_bits);
     if (ctx->P.ml_dlik) { cudaFree(ctx->P.ml_dlik); cudaFree(ctx->P.ml_dprior); cudaFree(ctx->P.ml_logq); cudaFree(ctx->P.ml_u); cudaFree(ctx->P.ml_acc); cudaFree(ctx->P.ml_U); }
@@ -431,8 +559,59 @@ int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, dou
 int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int64_t nrows, double cell_alpha,
                          int n_ktab, const void *ktab, const void *alphatab, const void *lgtab)
 {
-    if (!ctx) return PDG_E_ARG;
-    return fail(ctx, PDG_E_STATE, "log-linear scorer not built in this revision");
+    if (!ctx || !data || !levels || nrows < 1 || n_ktab < 0) return PDG_E_ARG;
+    if (n_ktab > 0 && (!ktab || !alphatab || !lgtab)) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PdgParams &P = ctx->P;
+    for (void *v : ctx->model_owned) cudaFree(v);
+    ctx->model_owned.clear();
+    auto own = [&](size_t bytes, void **out) -> cudaError_t {
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+        if (e == cudaSuccess) ctx->model_owned.push_back(*out);
+        return e;
+    };
+    void *d_data = nullptr, *d_lv = nullptr, *d_k = nullptr, *d_a = nullptr, *d_lg = nullptr;
+    CK(own((size_t)P.p * nrows, &d_data));
+    CK(own((size_t)P.p * sizeof(int), &d_lv));
+    CK(cudaMemcpyAsync(d_data, data, (size_t)P.p * nrows, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(d_lv, levels, (size_t)P.p * sizeof(int), cudaMemcpyDefault, ctx->stream));
+    if (n_ktab > 0) {
+        CK(own((size_t)n_ktab * 8, &d_k));
+        CK(own((size_t)n_ktab * 8, &d_a));
+        CK(own((size_t)n_ktab * (size_t)(nrows + 2) * 8, &d_lg));
+        CK(cudaMemcpyAsync(d_k, ktab, (size_t)n_ktab * 8, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(d_a, alphatab, (size_t)n_ktab * 8, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(d_lg, lgtab, (size_t)n_ktab * (size_t)(nrows + 2) * 8, cudaMemcpyDefault, ctx->stream));
+    }
+    // dense cell counters: one table per warp slot (= chain); larger sets go through a pool of
+    // hashed tables
+    int hist_cells = 1 << 16;
+    if (const char *v = getenv("PDG_HIST_CELLS")) { const int x = atoi(v); if (x >= 2) hist_cells = x; }
+    void *d_hist = nullptr;
+    CK(own((size_t)P.n_chains * hist_cells * 4, &d_hist));
+    CK(cudaMemsetAsync(d_hist, 0, (size_t)P.n_chains * hist_cells * 4, ctx->stream));
+    LoglinSparse sp;
+    sp.nsp = (int)(P.n_chains < 64 ? P.n_chains : 64);
+    int hs = 1;
+    while (hs < 2 * nrows) hs <<= 1;
+    sp.hslots = hs;
+    void *d_lock = nullptr, *d_hk = nullptr, *d_hc = nullptr, *d_cc = nullptr;
+    CK(own((size_t)sp.nsp * 4, &d_lock));
+    CK(own((size_t)sp.nsp * hs * 8, &d_hk));
+    CK(own((size_t)sp.nsp * hs * 4, &d_hc));
+    CK(own((size_t)sp.nsp * (size_t)(nrows + 2) * 4, &d_cc));
+    CK(cudaMemsetAsync(d_lock, 0, (size_t)sp.nsp * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_hk, 0, (size_t)sp.nsp * hs * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_hc, 0, (size_t)sp.nsp * hs * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_cc, 0, (size_t)sp.nsp * (size_t)(nrows + 2) * 4, ctx->stream));
+    sp.lock = (int *)d_lock; sp.hkeys = (u64 *)d_hk; sp.hcnt = (unsigned int *)d_hc; sp.cc = (unsigned int *)d_cc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    P.data = (const unsigned char *)d_data; P.levels = (const int *)d_lv; P.nrows = nrows; P.cell_alpha = cell_alpha;
+    P.n_ktab = n_ktab; P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
+    P.hist = (unsigned int *)d_hist; P.hist_cells = hist_cells; P.sp = sp;
+    P.model = PDG_MODEL_LOGLIN;
+    ctx->model_set = true;
+    return PDG_OK;
 }
 
 static int launch_derived(pdg_ctx *ctx, long long b, long long n)
@@ -518,18 +697,15 @@ int pdg_init_logl(pdg_ctx *ctx, int kind)
     if (!ctx) return PDG_E_ARG;
     if (!ctx->state_set || !ctx->model_set) return fail(ctx, PDG_E_STATE, "model/state not set");
     CK(cudaSetDevice(ctx->device));
-    const int NT = ctx->nwarps * 32;
-    const InitSmem L = init_smem_layout(ctx->P.p, ctx->P.W, ctx->nwarps);
     int rc;
-    if (ctx->P.model == PDG_MODEL_GGM) {
-        if ((rc = set_smem(ctx, k_init_logl<PDG_MODEL_GGM>, L.total))) return rc;
-        k_init_logl<PDG_MODEL_GGM><<<(unsigned)ctx->P.n_chains, NT, L.total, ctx->stream>>>(ctx->P, kind);
-    } else {
-        if ((rc = set_smem(ctx, k_init_logl<PDG_MODEL_UNIFORM>, L.total))) return rc;
-        k_init_logl<PDG_MODEL_UNIFORM><<<(unsigned)ctx->P.n_chains, NT, L.total, ctx->stream>>>(ctx->P, kind);
+    // a run starts with an empty memo: nothing scored in an earlier run is reused
+    if ((rc = memo_clear(ctx))) return rc;
+    switch (ctx->P.model) {
+    case PDG_MODEL_GGM: rc = launch_init_m<PDG_MODEL_GGM>(ctx, kind); break;
+    case PDG_MODEL_LOGLIN: rc = launch_init_m<PDG_MODEL_LOGLIN>(ctx, kind); break;
+    default: rc = launch_init_m<PDG_MODEL_UNIFORM>(ctx, kind); break;
     }
-    ctx->launches++;
-    CK(cudaGetLastError());
+    if (rc) return rc;
     k_snapshot_graph<<<(unsigned)ctx->P.n_chains, 32, 0, ctx->stream>>>(ctx->P);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -714,14 +890,13 @@ int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores)
     CK(cudaMalloc((void **)&d_err, 4));
     CK(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
     CK(cudaMemcpyAsync(d_bits, bits, (size_t)n_sets * P.W * 8, cudaMemcpyDefault, ctx->stream));
-    const int nw = ctx->nwarps;
-    long long grid = (n_sets + nw - 1) / nw;
-    if (grid > P.n_chains) grid = P.n_chains;      // the k > 32 scratch is sized per chain
-    const int sm = nw * 528 * 8 + nw * ((((P.p + 1) * 2 + 15) / 16) * 16);
-    if (P.model == PDG_MODEL_GGM) k_score_sets<PDG_MODEL_GGM><<<(unsigned)grid, nw * 32, sm, ctx->stream>>>(P, d_bits, n_sets, d_out, d_err);
-    else k_score_sets<PDG_MODEL_UNIFORM><<<(unsigned)grid, nw * 32, sm, ctx->stream>>>(P, d_bits, n_sets, d_out, d_err);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    int rc;
+    switch (P.model) {
+    case PDG_MODEL_GGM: rc = launch_score_m<PDG_MODEL_GGM>(ctx, d_bits, n_sets, d_out, d_err); break;
+    case PDG_MODEL_LOGLIN: rc = launch_score_m<PDG_MODEL_LOGLIN>(ctx, d_bits, n_sets, d_out, d_err); break;
+    default: rc = launch_score_m<PDG_MODEL_UNIFORM>(ctx, d_bits, n_sets, d_out, d_err); break;
+    }
+    if (rc) return rc;
     int herr = 0;
     CK(cudaMemcpyAsync(scores, d_out, (size_t)n_sets * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -779,15 +954,15 @@ int pdg_get_timing(pdg_ctx *ctx, double *ms_run, double *ms_randomize, int64_t *
     return PDG_OK;
 }
 
-int pdg_get_work(pdg_ctx *ctx, int64_t work[4])
+int pdg_get_work(pdg_ctx *ctx, int64_t work[8])
 {
     if (!ctx || !work) return PDG_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<unsigned long long> h((size_t)ctx->P.n_chains * 4);
+    std::vector<unsigned long long> h((size_t)ctx->P.n_chains * 8);
     CK(cudaMemcpy(h.data(), ctx->P.work, h.size() * 8, cudaMemcpyDeviceToHost));
-    for (int q = 0; q < 4; ++q) work[q] = 0;
-    for (size_t c = 0; c < (size_t)ctx->P.n_chains; ++c) for (int q = 0; q < 4; ++q) work[q] += (int64_t)h[c * 4 + q];
+    for (int q = 0; q < 8; ++q) work[q] = 0;
+    for (size_t c = 0; c < (size_t)ctx->P.n_chains; ++c) for (int q = 0; q < 8; ++q) work[q] += (int64_t)h[c * 8 + q];
     return PDG_OK;
 }
 

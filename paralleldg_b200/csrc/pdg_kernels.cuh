@@ -1,10 +1,40 @@
-// Kernels of the parallelDG B200 hot path.  One CTA owns one chain for the whole launch; the
-// per-chain junction-tree state (clique bit-matrix M, its transpose N, tree CSR) lives in
-// global memory laid out chain-major (L2 resident: 1024 chains x 64 KB at p = 500) and the
-// per-iteration scratch in shared memory.
+// Shared definitions of the parallelDG B200 kernels: launch parameters, the device-wide memo
+// table of clique scores, priors and the hyper-inverse-Wishart clique scorer.
+//
+// Memory layout in HBM (chain-major, SoA over chains):
+//   M  [chain][p][W] u64   clique bit-matrix  (t2clique, junction_tree.py:36-42)
+//   N  [chain][p][W] u64   its transpose       (node2t,  junction_tree.py:68-76)
+//   edges [chain][p-1][2] i32, csr_off [chain][p+1] u16, csr_adj [chain][2p] u16   the tree `t`
+//   logl [chain][n_samples] f64, rec/rec_bits [chain][rec_cap]  per-chain append buffers
+// and one memo table per GPU shared by every chain (all chains score the same data set).
 #pragma once
 #include "pdg_device.cuh"
 #include "../../include/pdg_b200.h"
+
+#define PDG_WMAX_LIMIT 8            // p <= 512
+#define MEMO_SENT 0x7FF8DEADBEEF0001ull
+#define MEMO_PROBES 16
+
+// Open-addressing memo of score(X), keyed by the bitset of the complete set X.  Values are a
+// canonical function of the key (ascending-index factorisation / cell order), so concurrent
+// writers store identical bits and a reader that races a writer merely recomputes.
+struct MemoTable {
+    ulonglong2 *kv;     // W == 1: {key, value bits}
+    u64 *tag;           // W  > 1: 64-bit hash tag (0 = empty), key words and value arrays
+    u64 *keyw;
+    u64 *val;
+    u32 mask;           // slots - 1
+    int W;
+};
+
+// pool of hashed cell tables for log-linear sets with more cells than the dense per-warp table
+struct LoglinSparse {
+    int *lock;              // [nsp]
+    u64 *hkeys;             // [nsp][hslots]
+    unsigned int *hcnt;     // [nsp][hslots]
+    unsigned int *cc;       // [nsp][nrows + 2] count-of-counts
+    int nsp, hslots;
+};
 
 struct PdgParams {
     int p, W;
@@ -22,8 +52,20 @@ struct PdgParams {
     const double *A, *Dm, *logDdiag, *gconst;
     int dmode;                  // 0 identity, 1 diagonal, 2 general
     double delta, nobs;
-    double *big;                // [chain][warp] packed triangles for cliques > 32
+    double *big;                // [warp slot] packed triangles for cliques > 32
     int kbig;                   // largest clique the scratch supports
+    // log-linear
+    const unsigned char *data;  // [p][nrows] level codes, column-major
+    const int *levels;          // [p]
+    long long nrows;
+    double cell_alpha;
+    int n_ktab;                 // lgamma tables: ktab[j] = cells, alphatab[j], lgtab[j][c]
+    const double *ktab, *alphatab, *lgtab;
+    double ll_const;            // lgamma(N + cell_alpha) - lgamma(cell_alpha)
+    unsigned int *hist;         // [warp slot][hist_cells] dense cell counters
+    int hist_cells;
+    LoglinSparse sp;
+    MemoTable memo;
     // outputs
     double *logl;               // [chain][n_samples]
     long long *kcount, *nrec;   // [chain]
@@ -31,7 +73,7 @@ struct PdgParams {
     u64 *rec_bits;              // [chain][rec_cap][2][W]
     long long rec_cap;
     int *err;                   // [chain]
-    unsigned long long *work;   // [chain][4]: bytes, 6*flops, scored sets, sum k
+    unsigned long long *work;   // [chain][8]: see pdg_get_work
     u64 *G0;                    // [chain][p][W] graph adjacency at MCMC index 0 (for edge tallies)
     // per-proposal diagnostics (optional)
     long long mvlog_cap;
@@ -71,6 +113,100 @@ __device__ __forceinline__ double prior_partial(const PdgParams &P, int csize, i
     }
 }
 
+// ---- memo table --------------------------------------------------------------------------
+__device__ __forceinline__ u64 mix64(u64 k)
+{
+    k ^= k >> 30; k *= 0xBF58476D1CE4E5B9ull;
+    k ^= k >> 27; k *= 0x94D049BB133111EBull;
+    k ^= k >> 31;
+    return k;
+}
+
+template <int WMAX>
+__device__ __forceinline__ u64 key_hash(const u64 (&X)[WMAX], int W)
+{
+    u64 h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) if (w < W) h = mix64(h ^ X[w]);
+    return h;
+}
+
+template <int WMAX>
+__device__ __forceinline__ bool memo_lookup(const MemoTable &T, const u64 (&X)[WMAX], int W, double &val)
+{
+    if (WMAX == 1) {
+        u32 h = (u32)mix64(X[0]) & T.mask;
+        for (int pr = 0; pr < MEMO_PROBES; ++pr) {
+            const ulonglong2 e = __ldcg(&T.kv[h]);
+            if (e.x == X[0]) {
+                if (e.y == MEMO_SENT) return false;
+                val = __longlong_as_double((long long)e.y);
+                return true;
+            }
+            if (e.x == 0ull) return false;
+            h = (h + 1) & T.mask;
+        }
+        return false;
+    } else {
+        const u64 hh = key_hash<WMAX>(X, W);
+        const u64 tag = hh | 1ull;
+        u32 h = (u32)(hh >> 32) & T.mask;
+        for (int pr = 0; pr < MEMO_PROBES; ++pr) {
+            const u64 t = __ldcg(&T.tag[h]);
+            if (t == 0ull) return false;
+            if (t == tag) {
+                bool same = true;
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) if (w < W) same = same && (__ldcg(&T.keyw[(size_t)h * W + w]) == X[w]);
+                if (same) {
+                    const u64 v = __ldcg(&T.val[h]);
+                    if (v == MEMO_SENT) return false;
+                    val = __longlong_as_double((long long)v);
+                    return true;
+                }
+            }
+            h = (h + 1) & T.mask;
+        }
+        return false;
+    }
+}
+
+template <int WMAX>
+__device__ __forceinline__ void memo_insert(const MemoTable &T, const u64 (&X)[WMAX], int W, double val)
+{
+    const u64 vb = (u64)__double_as_longlong(val);
+    if (WMAX == 1) {
+        u32 h = (u32)mix64(X[0]) & T.mask;
+        for (int pr = 0; pr < MEMO_PROBES; ++pr) {
+            const u64 old = atomicCAS(&T.kv[h].x, 0ull, X[0]);
+            if (old == 0ull || old == X[0]) { __stcg(&T.kv[h].y, vb); return; }
+            h = (h + 1) & T.mask;
+        }
+    } else {
+        const u64 hh = key_hash<WMAX>(X, W);
+        const u64 tag = hh | 1ull;
+        u32 h = (u32)(hh >> 32) & T.mask;
+        for (int pr = 0; pr < MEMO_PROBES; ++pr) {
+            const u64 old = atomicCAS(&T.tag[h], 0ull, tag);
+            if (old == 0ull) {
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) if (w < W) __stcg(&T.keyw[(size_t)h * W + w], X[w]);
+                __threadfence();
+                __stcg(&T.val[h], vb);
+                return;
+            }
+            if (old == tag) {
+                bool same = true;
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) if (w < W) same = same && (__ldcg(&T.keyw[(size_t)h * W + w]) == X[w]);
+                if (same) { __stcg(&T.val[h], vb); return; }
+            }
+            h = (h + 1) & T.mask;
+        }
+    }
+}
+
+// ---- hyper-inverse-Wishart clique score ------------------------------------------------------
 // ggm:26-39 with wishart.py:17-37 folded: score(X) = gconst[k] - t1 ld(A_XX) + t2 ld(D_XX)
 __device__ __forceinline__ double ggm_score_from(const PdgParams &P, int k, double ldA, double ldD)
 {
@@ -88,110 +224,163 @@ struct WarpScratch {
     int kbig;
 };
 
-// fills idx[0..k) = [S0 | B\S0 | v?] from the two bit rows; returns kb, ks through refs
-__device__ __forceinline__ void build_index(const u64 *Crow, const u64 *Adjrow, int node, bool with_v,
-                                            int W, int lane, short *idx, int &kb, int &ks)
+// idx[rank] = g for every set bit g of the key, ascending (rank by popcount of lower bits)
+template <int WMAX>
+__device__ __forceinline__ int build_index_sorted(const u64 (&X)[WMAX], int W, int lane, short *idx)
 {
-    int cb = 0, cs = 0;
-    for (int w = 0; w < W; ++w) {
-        u64 b = Crow[w];
-        if (node >= 0 && (node >> 6) == w) b &= ~(1ull << (node & 63));
-        const u64 s = Adjrow ? (b & Adjrow[w]) : 0ull;
-        cb += __popcll(b);
-        cs += __popcll(s);
-    }
-    kb = cb; ks = cs;
-    const int k = cb + (with_v ? 1 : 0);
-    for (int i = lane; i < k; i += 32) {
-        int g;
-        if (i >= cb) g = node;
-        else {
-            const bool inS = i < cs;
-            int n = inS ? i : i - cs;
-            g = -1;
-            for (int w = 0; w < W; ++w) {
-                u64 b = Crow[w];
-                if (node >= 0 && (node >> 6) == w) b &= ~(1ull << (node & 63));
-                const u64 s = Adjrow ? (b & Adjrow[w]) : 0ull;
-                const u64 x = inS ? s : (b & ~s);
-                const int c = __popcll(x);
-                if (n < c) { g = w * 64 + select64(x, n); break; }
-                n -= c;
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+        if (w < W) {
+            const u64 x = X[w];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int b = half * 32 + lane;
+                if ((x >> b) & 1ull) idx[base + __popcll(x & ((1ull << b) - 1ull))] = (short)(w * 64 + b);
             }
+            base += __popcll(x);
         }
-        idx[i] = (short)g;
     }
     __syncwarp();
+    return base;
 }
 
-// gathers the packed lower triangle of mat[idx, idx] and factorises it
+// gathers the packed lower triangle of mat[idx, idx] and factorises it (LDL^T, see pdg_device.cuh)
 __device__ __forceinline__ bool gather_ldl(const double *__restrict__ mat, int p, double *a, const short *idx,
-                                           int lane, int k, int ks, int kb,
-                                           double &sumS, double &sumB, double &ldv, double &lschur)
+                                           int lane, int k, double &logdet)
 {
     for (int i = lane; i < k; i += 32) {
         const double *row = mat + (size_t)idx[i] * p;
         double *dst = a + tri(i, 0);
         for (int l = 0; l <= i; ++l) dst[l] = __ldg(row + idx[l]);
     }
-    return ldl_logdets(a, lane, k, ks, kb, sumS, sumB, ldv, lschur);
+    double sS, ldv, lsc;
+    return ldl_logdets(a, lane, k, 0, k, sS, logdet, ldv, lsc);
 }
 
-// Scores the four complete sets of one move with a single factorisation (see ldl_logdets).
-// out[0] = score(B), out[1] = score(S0), out[2] = score(B+v), out[3] = score(S0+v).
+// canonical score of one complete set (ascending vertex order); whole warp cooperates.
 // Returns 0 or an ERR_* bit.
-__device__ __forceinline__ int ggm_move_scores(const PdgParams &P, const WarpScratch &ws, const u64 *Crow,
-                                               const u64 *Adjrow, int node, int lane, int &kb, int &ks,
-                                               double out[4])
-{
-    build_index(Crow, Adjrow, node, true, P.W, lane, ws.idx, kb, ks);
-    const int k = kb + 1;
-    double *a = ws.tri32;
-    if (k > 32) {
-        if (!ws.big || k > ws.kbig) return ERR_BIGCLIQUE;
-        a = ws.big;
-    }
-    double sS, sB, ldv, lsc;
-    if (!gather_ldl(P.A, P.p, a, ws.idx, lane, k, ks, kb, sS, sB, ldv, lsc)) return ERR_NUMERIC;
-    double dS = 0.0, dB = 0.0, dv = 0.0, dsc = 0.0;
-    if (P.dmode == 1) {
-        double accS = 0.0, accB = 0.0;
-        for (int j = lane; j < kb; j += 32) { const double l = P.logDdiag[ws.idx[j]]; accB += l; if (j < ks) accS += l; }
-        dS = warp_sum(accS); dB = warp_sum(accB); dv = P.logDdiag[node]; dsc = dv;
-    } else if (P.dmode == 2) {
-        if (!gather_ldl(P.Dm, P.p, a, ws.idx, lane, k, ks, kb, dS, dB, dv, dsc)) return ERR_NUMERIC;
-    }
-    out[0] = ggm_score_from(P, kb, sB, dB);
-    out[1] = ggm_score_from(P, ks, sS, dS);
-    out[2] = ggm_score_from(P, kb + 1, sB + ldv, dB + dv);
-    out[3] = ggm_score_from(P, ks + 1, sS + lsc, dS + dsc);
-    return 0;
-}
-
-// score of one complete set given as a bit row (used for logl[0] and the batch scorer)
-__device__ __forceinline__ int ggm_set_score(const PdgParams &P, const WarpScratch &ws, const u64 *row, int lane,
+template <int WMAX>
+__device__ __forceinline__ int ggm_set_score(const PdgParams &P, const WarpScratch &ws, const u64 (&X)[WMAX], int lane,
                                              double &score)
 {
-    int kb, ks;
-    build_index(row, nullptr, -1, false, P.W, lane, ws.idx, kb, ks);
-    const int k = kb;
+    const int k = build_index_sorted<WMAX>(X, P.W, lane, ws.idx);
     if (k == 0) { score = 0.0; return 0; }
     double *a = ws.tri32;
     if (k > 32) {
         if (!ws.big || k > ws.kbig) return ERR_BIGCLIQUE;
         a = ws.big;
     }
-    double sS, sB, ldv, lsc;
-    if (!gather_ldl(P.A, P.p, a, ws.idx, lane, k, 0, k, sS, sB, ldv, lsc)) return ERR_NUMERIC;
-    double dB = 0.0;
+    double ldA, ldD = 0.0;
+    if (!gather_ldl(P.A, P.p, a, ws.idx, lane, k, ldA)) return ERR_NUMERIC;
     if (P.dmode == 1) {
         double acc = 0.0;
         for (int j = lane; j < k; j += 32) acc += P.logDdiag[ws.idx[j]];
-        dB = warp_sum(acc);
+        ldD = warp_sum(acc);
     } else if (P.dmode == 2) {
-        double t0, t1, t2;
-        if (!gather_ldl(P.Dm, P.p, a, ws.idx, lane, k, 0, k, t0, dB, t1, t2)) return ERR_NUMERIC;
+        if (!gather_ldl(P.Dm, P.p, a, ws.idx, lane, k, ldD)) return ERR_NUMERIC;
     }
-    score = ggm_score_from(P, k, sB, dB);
+    score = ggm_score_from(P, k, ldA, ldD);
     return 0;
+}
+
+// ---- lane-private scorer for small cliques ---------------------------------------------------
+// Cliques met by the sampler are small (mean 4-5 vertices), so the batched scorer gives every
+// LANE its own complete set and factorises it in REGISTERS: the packed lower triangle of
+// A[X, X] is gathered with fully unrolled, statically indexed code and reduced by a right-looking
+// LDL^T in ascending vertex order.  All lanes of the warp run the same straight-line code for
+// K = 4 or 8, whichever covers the warp-wide largest set; smaller sets are padded with identity rows,
+// which leaves every operation on the real block -- and therefore the result bit pattern --
+// unchanged, so score(X) stays a pure function of X.  32 scores per warp pass, no shared memory.
+#define PDG_KT 8                        // largest clique of the lane-private path
+
+struct LaneScratch { int unused; };
+
+// One inlined copy per K: the (rare) general-D case reuses the same code through a rolled
+// two-pass loop, which keeps the hot loop small (the MH kernel is instruction-cache sensitive:
+// 32 KB L1.5 I-cache, several warps per SM at different program counters) and every array in
+// registers.
+template <int K, int WMAX>
+__device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&X)[WMAX], int k, double &score)
+{
+    int idx[K];
+    u64 Y[WMAX];
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) Y[w] = X[w];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        int g = 0;
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) {
+            if (!found && Y[w]) { g = w * 64 + __ffsll((long long)Y[w]) - 1; Y[w] &= Y[w] - 1; found = true; }
+        }
+        idx[t] = g;
+    }
+    double ld[2] = {0.0, 0.0};
+    bool ok = true;
+    const int npass = (P.dmode == 2) ? 2 : 1;
+    const int p = P.p;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+        const double *__restrict__ mat = pass ? P.Dm : P.A;
+        double a[K * (K + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const double *row = mat + (size_t)idx[i] * p;
+#pragma unroll
+            for (int l = 0; l <= i; ++l) {
+                double v = (i == l) ? 1.0 : 0.0;
+                if (i < k) v = __ldg(row + idx[l]);
+                a[i * (i + 1) / 2 + l] = v;
+            }
+        }
+        double prod = 1.0, piv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double d = a[j * (j + 1) / 2 + j];
+            piv[j] = d;
+            ok = ok && (d > 0.0);
+            prod *= d;
+            const double inv = 1.0 / d;
+#pragma unroll
+            for (int i = j + 1; i < K; ++i) {
+                const double f = a[i * (i + 1) / 2 + j] * inv;
+#pragma unroll
+                for (int l = j + 1; l <= i; ++l) a[i * (i + 1) / 2 + l] -= f * a[l * (l + 1) / 2 + j];
+            }
+        }
+        double v;
+        if (prod > 1e-280 && prod < 1e280) v = log(prod);
+        else {                               // product left the double range: sum the logs instead
+            v = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) v += log(piv[j]);
+        }
+        ld[pass] = v;
+    }
+    if (P.dmode == 1) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) if (j < k) ld[1] += P.logDdiag[idx[j]];
+    }
+    score = ggm_score_from(P, k, ld[0], ld[1]);
+    return (ok || k == 0) ? 0 : ERR_NUMERIC;
+}
+
+// scores of the lanes' own sets; k = |X| for lanes that need one (<= PDG_KT), 0 for the others.
+// Warp-uniform dispatch on the largest k.
+template <int WMAX>
+__device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const u64 (&X)[WMAX], int k, double &score)
+{
+    const int kmax = (int)__reduce_max_sync(PDG_FULL, (unsigned)k);
+    if (kmax == 0) { score = 0.0; return 0; }
+    if (kmax <= 4) return ggm_lane_score_k<4, WMAX>(P, X, k, score);
+    return ggm_lane_score_k<8, WMAX>(P, X, k, score);
+}
+
+template <int WMAX>
+__device__ __forceinline__ void load_row(u64 (&X)[WMAX], const u64 *row, int W)
+{
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) X[w] = (w < W) ? row[w] : 0ull;
 }

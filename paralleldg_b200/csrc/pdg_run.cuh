@@ -1,64 +1,126 @@
-// The fused Metropolis-Hastings kernel: proposal enumeration on the latent tree, clique scoring,
-// Philox accept/reject, state update and update-record append, for iterations [it_begin, it_end)
-// of every chain (one CTA per chain).  Restates mh_parallel.py:225-304 (parallel moves) and
-// :66-168 (single move) with python sets replaced by ballot-built bitsets.
+// The fused Metropolis-Hastings kernel.  ONE WARP owns one chain for iterations [it_begin,
+// it_end): proposal enumeration on the latent tree (ballot/popc bitsets), clique scoring through
+// the device-wide memo table, Philox accept/reject, state update and update-record append.
+// Restates mh_parallel.py:225-304 (parallel moves) and :66-168 (single move).
+//
+// Lane mapping inside an iteration:
+//   enumeration : lane <-> tree node (32 per pass)
+//   scoring     : lane = 4 * move + set; the four complete sets of a move are
+//                 set 0 = B = C - {v}, 1 = S0 = B & Cadj, 2 = B + v, 3 = S0 + v
+//                 (connect: C = B, Cnew = B + v; disconnect: C = B + v, Cnew = B), so eight
+//                 proposals are looked up / accepted per pass with no idle half-warps
+//   memo misses : the whole warp factorises (GGM) or counts (log-linear) one set at a time
 #pragma once
 #include "pdg_kernels.cuh"
+#include "pdg_loglin.cuh"
 
-// shared-memory carve-up, identical on host and device
 struct RunSmem {
-    int off_tri, off_idx, off_delta, off_dl, off_dp, off_u, off_sub, off_leaf, off_bnd, off_partner,
-        off_mvU, off_mvUadj, off_acc, off_csr_off, off_csr_adj, off_work, total;
+    int off_tri, off_idx, off_sub, off_leaf, off_bnd, off_partner, off_mvU, off_mvUadj, off_csr_off, off_csr_adj,
+        off_M, off_N, off_lidx, total;
 };
 
-__host__ __device__ inline RunSmem run_smem_layout(int p, int W, int nwarps)
+__host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state)
 {
     RunSmem s;
     int o = 0;
-    const int np32 = ((p + 31) / 32) + 1;
-    s.off_tri = o;      o += nwarps * 528 * 8;
-    s.off_work = o;     o += nwarps * 4 * 8;
-    s.off_delta = o;    o += p * 8;
-    s.off_dl = o;       o += p * 8;
-    s.off_dp = o;       o += p * 8;
-    s.off_u = o;        o += p * 8;
-    s.off_sub = o;      o += ((W * 8 + 15) / 16) * 16;
-    s.off_leaf = o;     o += ((np32 * 4 + 15) / 16) * 16;
-    s.off_bnd = o;      o += ((np32 * 4 + 15) / 16) * 16;
-    s.off_idx = o;      o += nwarps * (((p + 1) * 2 + 15) / 16) * 16;
-    s.off_partner = o;  o += ((p * 2 + 15) / 16) * 16;
-    s.off_mvU = o;      o += ((p * 2 + 15) / 16) * 16;
-    s.off_mvUadj = o;   o += ((p * 2 + 15) / 16) * 16;
-    s.off_csr_off = o;  o += (((p + 1) * 2 + 15) / 16) * 16;
-    s.off_csr_adj = o;  o += ((2 * p * 2 + 15) / 16) * 16;
-    s.off_acc = o;      o += ((p + 15) / 16) * 16;
-    s.total = o;
+    const int np32 = 2 * W + 2;
+    const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
+    s.off_tri = o;      o += 528 * 8;
+    s.off_lidx = o;
+    s.off_sub = o;      o += W * 8;
+    s.off_M = o;        o += smem_state ? p * W * 8 : 0;
+    s.off_N = o;        o += smem_state ? p * W * 8 : 0;
+    s.off_leaf = o;     o += (np32 * 4 + 15) / 16 * 16;
+    s.off_bnd = o;      o += (np32 * 4 + 15) / 16 * 16;
+    s.off_idx = o;      o += a2;
+    s.off_partner = o;  o += a2;
+    s.off_mvU = o;      o += a2;
+    s.off_mvUadj = o;   o += a2;
+    s.off_csr_off = o;  o += a2;
+    s.off_csr_adj = o;  o += 2 * a2;
+    s.total = (o + 15) / 16 * 16;
     return s;
 }
 
-// n-th set bit of a multi-word (32-bit words) bitset
-__device__ __forceinline__ int select_multi32(const u32 *w, int nwords, int n)
+// Scores of up to 32 complete sets, one per lane (`need` lanes carry a key each).
+//   GGM, |X| <= PDG_KT : every lane factorises its own set (no communication)
+//   otherwise          : memo table; the warp resolves the misses one after the other with the
+//                        cooperative scorers (32-row LDL^T / contingency-table scan)
+// Returns the ERR_* bits raised.
+template <int MODEL, int WMAX>
+__device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
+                                           int lane, const u64 (&X)[WMAX], bool need, double &score,
+                                           unsigned long long (&wk)[8])
 {
-    for (int i = 0; i < nwords; ++i) {
-        const int c = __popc(w[i]);
-        if (n < c) return i * 32 + select32(w[i], n);
-        n -= c;
+    const int W = P.W;
+    int err = 0;
+    bool hit = true;
+    score = 0.0;
+    int kq = 0;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) kq += __popcll(X[w]);
+    if (need) { wk[4] += 1ull; wk[5] += (unsigned long long)kq; }
+    if (MODEL == PDG_MODEL_GGM) {
+        const bool small = need && kq <= PDG_KT;
+        double s_small = 0.0;
+        err |= ggm_lane_scores<WMAX>(P, X, small ? kq : 0, s_small);
+        if (small) {
+            score = s_small;
+            const unsigned long long kk = (unsigned long long)kq, dm = (P.dmode == 2 ? 2ull : 1ull);
+            wk[0] += 8ull * kk * kk * dm;
+            wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * dm;
+            wk[2] += 1ull; wk[3] += kk;
+        }
+        need = need && !small;
+        __syncwarp();
     }
-    return -1;
+    if (need) hit = memo_lookup<WMAX>(P.memo, X, W, score);
+    u32 miss = __ballot_sync(PDG_FULL, need && !hit);
+    while (miss) {
+        const int src = __ffs((int)miss) - 1;
+        u64 Y[WMAX];
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) Y[w] = __shfl_sync(PDG_FULL, X[w], src);
+        double sc = 0.0;
+        int e;
+        if (MODEL == PDG_MODEL_GGM) e = ggm_set_score<WMAX>(P, ws, Y, lane, sc);
+        else e = loglin_set_score<WMAX>(P, ws, slot, Y, lane, sc);
+        err |= e;
+        if (lane == 0) {
+            if (!e) memo_insert<WMAX>(P.memo, Y, W, sc);
+            int k = 0;
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w) k += __popcll(Y[w]);
+            const unsigned long long kk = (unsigned long long)k;
+            if (MODEL == PDG_MODEL_GGM) {
+                wk[0] += 8ull * kk * kk * (P.dmode == 2 ? 2ull : 1ull);
+                wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * (P.dmode == 2 ? 2ull : 1ull);
+            } else {
+                wk[0] += (unsigned long long)P.nrows * kk;
+            }
+            wk[2] += 1ull; wk[3] += kk;
+        }
+        // every lane waiting for this very key takes the value
+        bool same = need && !hit;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) same = same && (X[w] == Y[w]);
+        if (same) { score = sc; hit = true; }
+        miss = __ballot_sync(PDG_FULL, need && !hit);
+    }
+    return err;
 }
 
-template <int MODEL, int KIND>
-__global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin, long long it_end, PdgReplayDev R)
+template <int MODEL, int WMAX, bool SMEM_STATE>
+__global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long it_begin, long long it_end,
+                                                PdgReplayDev R, int lockstep)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
     const int p = P.p, W = P.W;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nw = NT >> 5;
-    const long long chain = blockIdx.x;
-    const RunSmem L = run_smem_layout(p, W, nw);
-    double *s_delta = (double *)(smem + L.off_delta);
-    double *s_dl = (double *)(smem + L.off_dl);
-    double *s_dp = (double *)(smem + L.off_dp);
-    double *s_u = (double *)(smem + L.off_u);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const long long chain = (long long)blockIdx.x * wpc + warp;
+    if (chain >= P.n_chains) return;                       // (lockstep is only set when no warp exits here)
+    const RunSmem L = run_smem_layout(p, W, SMEM_STATE);
+    unsigned char *smem = smem_all + (size_t)warp * L.total;
     u64 *s_sub = (u64 *)(smem + L.off_sub);
     u32 *s_sub32 = (u32 *)(smem + L.off_sub);
     u32 *s_leaf = (u32 *)(smem + L.off_leaf);
@@ -66,31 +128,40 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
     short *s_partner = (short *)(smem + L.off_partner);
     short *s_mvU = (short *)(smem + L.off_mvU);
     short *s_mvUadj = (short *)(smem + L.off_mvUadj);
-    unsigned char *s_acc = (unsigned char *)(smem + L.off_acc);
     unsigned short *s_off = (unsigned short *)(smem + L.off_csr_off);
     unsigned short *s_adj = (unsigned short *)(smem + L.off_csr_adj);
     WarpScratch ws;
-    ws.tri32 = (double *)(smem + L.off_tri) + warp * 528;
-    ws.idx = (short *)(smem + L.off_idx) + warp * ((((p + 1) * 2 + 15) / 16) * 8);
+    ws.tri32 = (double *)(smem + L.off_tri);
+    ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;
-    ws.big = P.big ? P.big + ((size_t)chain * nw + warp) * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    const int slot = (int)chain;                           // scratch slot of this warp
+    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    LaneScratch ls;
+    ls.unused = 0;
 
-    u64 *Mc = P.M + (size_t)chain * p * W;
-    u64 *Nc = P.N + (size_t)chain * p * W;
-    for (int i = tid; i <= p; i += NT) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
-    for (int i = tid; i < 2 * (p - 1); i += NT) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
-    const int nw32 = (p + 31) >> 5;
+    u64 *Mg = P.M + (size_t)chain * p * W;
+    u64 *Ng = P.N + (size_t)chain * p * W;
+    u64 *Mc = SMEM_STATE ? (u64 *)(smem + L.off_M) : Mg;
+    u64 *Nc = SMEM_STATE ? (u64 *)(smem + L.off_N) : Ng;
+    for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
+    for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
+    if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; }
+    __syncwarp();
+
     const u32 gchain = P.chain0 + (u32)chain;
     long long k = P.kcount[chain];
     long long nrec = P.nrec[chain];
     double logl_prev = P.logl[(size_t)chain * P.n_samples + it_begin - 1];
     int errflag = 0;
-    const int npass = (p + NT - 1) / NT;
-    unsigned long long *s_work = (unsigned long long *)(smem + L.off_work) + warp * 4;
-    if (lane < 4) s_work[lane] = 0ull;
+    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    const u32 lt = (1u << lane) - 1u;
+    const int nw32 = (p + 31) >> 5;
 
     for (long long it = it_begin; it < it_end; ++it) {
-        // ---- draws (mh_parallel.py:230-231) -------------------------------------------
+        // chains of one CTA start every iteration together: the loop body is larger than the
+        // L1.5 instruction cache, in step the warps share its fetches instead of each streaming it
+        if (lockstep) __syncthreads();
+        // ---- draws (mh_parallel.py:230-231) -------------------------------------------------
         int node, mtype, aux = -1;
         u32 r[4] = {0u, 0u, 0u, 0u};
         if (R.on) {
@@ -101,20 +172,24 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
             node = (int)__umulhi(r[0], (u32)p);
             mtype = (int)(r[1] >> 31);
         }
-        if (tid < W) s_sub[tid] = Nc[(size_t)node * W + tid];
-        __syncthreads();
+        if (lane < W) s_sub[lane] = Nc[(size_t)node * W + lane];
+        __syncwarp();
         int msub = 0;
-        for (int w = 0; w < W; ++w) msub += __popcll(s_sub[w]);
-        if (msub == 0) mtype = 0;          // :237-240 forced move types
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) if (w < W) msub += __popcll(s_sub[w]);
+        if (msub == 0) mtype = 0;            // :237-240 forced move types
         if (msub == p) mtype = 1;
-        // ---- one scan of the tree: leaves of the induced subtree and its outer boundary ----
-        // (parallel_moves.py:193-208 and :253-272)
-        for (int ps = 0; ps < npass; ++ps) {
-            const int t = ps * NT + tid;
+        const bool special = (mtype == 0 && msub == 0) || (mtype == 1 && msub <= 2);
+        // ---- one pass over the tree: leaves of the induced subtree / its outer boundary ------
+        // (parallel_moves.py:193-208 and :253-272); proposals come out in ascending tree-node order
+        int nm = 0, nleaf = 0, nbnd = 0;
+        for (int base = 0; base < p; base += 32) {
+            const int t = base + lane;
             bool leaf = false, bnd = false;
+            int last = -1;
             if (t < p) {
                 const int inT = bit32(s_sub32, t);
-                int cnt = 0, last = -1;
+                int cnt = 0;
                 for (int e = s_off[t]; e < s_off[t + 1]; ++e) {
                     const int a = s_adj[e];
                     if (bit32(s_sub32, a)) { ++cnt; last = a; }
@@ -124,140 +199,131 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
                 s_partner[t] = (short)last;
             }
             const u32 bl = __ballot_sync(PDG_FULL, leaf), bb = __ballot_sync(PDG_FULL, bnd);
-            if (lane == 0 && (ps * NT + warp * 32) < nw32 * 32) { s_leaf[(ps * NT >> 5) + warp] = bl; s_bnd[(ps * NT >> 5) + warp] = bb; }
+            if (lane == 0) { s_leaf[base >> 5] = bl; s_bnd[base >> 5] = bb; }
+            nleaf += __popc(bl); nbnd += __popc(bb);
+            const u32 fl = mtype == 0 ? bb : bl;
+            if (!special && ((fl >> lane) & 1u)) {
+                const int pos = nm + __popc(fl & lt);
+                s_mvU[pos] = (short)t; s_mvUadj[pos] = (short)last;
+            }
+            nm += __popc(fl);
         }
-        __syncthreads();
-        // ---- ordered proposal list ------------------------------------------------------
-        int nm, nfwd;
+        __syncwarp();
+        int nfwd = nm;
         double logq = 0.0;
         const u32 *set = (mtype == 0) ? s_bnd : s_leaf;
-        int nset = 0;
-        for (int i = 0; i < nw32; ++i) nset += __popc(set[i]);
-        const bool special = (mtype == 0 && msub == 0) || (mtype == 1 && msub <= 2);
         if (special) {
             nm = 1;
-            if (tid == 0) {
-                if (mtype == 0) {                       // pm:138-139 one random tree node
+            if (lane == 0) {
+                if (mtype == 0) {                         // pm:138-139 one random tree node
                     s_mvU[0] = (short)(R.on ? aux : (int)__umulhi(r[2], (u32)p));
                     s_mvUadj[0] = -1;
-                } else if (msub == 1) {                 // pm:186-187
-                    s_mvU[0] = (short)select_multi32(s_sub32, nw32, 0);
-                    s_mvUadj[0] = -1;
-                } else {                                // pm:184-185 one of the two leaves
-                    const int a = select_multi32(s_sub32, nw32, 0), b = select_multi32(s_sub32, nw32, 1);
-                    int pick;
-                    if (R.on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) errflag |= ERR_REPLAY; }
-                    else pick = (int)(r[2] >> 31);
-                    s_mvU[0] = (short)(pick ? b : a);
-                    s_mvUadj[0] = (short)(pick ? a : b);
+                } else {
+                    int a = -1, b = -1;
+                    for (int i = 0; i < nw32; ++i) {
+                        u32 x = s_sub32[i];
+                        while (x) { const int t = i * 32 + __ffs((int)x) - 1; x &= x - 1; if (a < 0) a = t; else if (b < 0) b = t; }
+                    }
+                    if (msub == 1) { s_mvU[0] = (short)a; s_mvUadj[0] = -1; }          // pm:186-187
+                    else {                                  // pm:184-185 one of the two leaves
+                        int pick;
+                        if (R.on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) errflag |= ERR_REPLAY; }
+                        else pick = (int)(r[2] >> 31);
+                        s_mvU[0] = (short)(pick ? b : a);
+                        s_mvUadj[0] = (short)(pick ? a : b);
+                    }
                 }
             }
             nfwd = (mtype == 1 && msub == 2) ? 2 : 1;
-            if (KIND == PDG_KIND_PARALLEL && mtype == 1 && msub == 2) logq = -0.6931471805599453;   // :277
-        } else {
-            nm = nset; nfwd = nset;
-            if (KIND == PDG_KIND_PARALLEL) {
-                if (R.on) {
-                    // the reference's ORDER (python set iteration) with the SET checked here
-                    const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
-                    const long long cnt = R.it_off[(size_t)chain * (R.n_samples + 1) + it + 1] - o;
-                    if (cnt != nm) { errflag |= ERR_REPLAY; nm = (int)(cnt < nm ? cnt : nm); }
-                    for (int j = tid; j < nm; j += NT) {
-                        const int U = R.mv_U[o + j], Ua = R.mv_Uadj[o + j];
-                        if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
-                        s_mvU[j] = (short)U; s_mvUadj[j] = (short)Ua;
-                    }
-                } else {
-                    for (int j = tid; j < nm; j += NT) {
-                        const int U = select_multi32(set, nw32, j);
-                        s_mvU[j] = (short)U; s_mvUadj[j] = s_partner[U];
-                    }
+            if (kind == PDG_KIND_PARALLEL && mtype == 1 && msub == 2) logq = -0.6931471805599453;   // :277
+        } else if (kind == PDG_KIND_PARALLEL) {
+            if (R.on) {
+                // the reference's ORDER (python set iteration); the SET is checked against ours
+                const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
+                const long long cnt = R.it_off[(size_t)chain * (R.n_samples + 1) + it + 1] - o;
+                if (cnt != nm) { errflag |= ERR_REPLAY; nm = (int)(cnt < nm ? cnt : nm); }
+                __syncwarp();
+                for (int j = lane; j < nm; j += 32) {
+                    const int U = R.mv_U[o + j], Ua = R.mv_Uadj[o + j];
+                    if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
+                    s_mvU[j] = (short)U; s_mvUadj[j] = (short)Ua;
                 }
-            } else {
-                // single move: moves[0] after np.random.shuffle (:87,:95 / :128,:138)
-                if (tid == 0) {
-                    int U, Ua;
-                    if (R.on) {
-                        const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
-                        U = R.mv_U[o]; Ua = R.mv_Uadj[o];
-                        if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
-                    } else {
-                        const int pick = nset > 1 ? (int)__umulhi(r[3], (u32)nset) : 0;
-                        U = select_multi32(set, nw32, pick); Ua = s_partner[U];
-                    }
-                    s_mvU[0] = (short)U; s_mvUadj[0] = (short)Ua;
-                }
-                nm = 1;
             }
+        } else {
+            // single move: moves[0] after np.random.shuffle (:87,:95 / :128,:138)
+            int U, Ua;
+            if (R.on) {
+                const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
+                U = R.mv_U[o]; Ua = R.mv_Uadj[o];
+                if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
+            } else {
+                const int pick = nm > 1 ? (int)__umulhi(r[3], (u32)nm) : 0;
+                U = s_mvU[pick]; Ua = s_mvUadj[pick];
+            }
+            __syncwarp();
+            if (lane == 0) { s_mvU[0] = (short)U; s_mvUadj[0] = (short)Ua; }
+            nm = 1;
         }
-        __syncthreads();
-        if (KIND == PDG_KIND_SINGLE) {
+        __syncwarp();
+        if (kind == PDG_KIND_SINGLE) {
             // Hastings term log_q2 - log_q1 = -log(num_moves) + log(num_reverse)  (:111-118, :154-160)
             const int U = s_mvU[0], Ua = s_mvUadj[0];
             int nrev;
             if (mtype == 0) {
-                int nl = 0;
-                if (msub >= 2) for (int i = 0; i < nw32; ++i) nl += __popc(s_leaf[i]);
+                const int nl = msub >= 2 ? nleaf : 0;
                 const int notin = (Ua >= 0 && msub >= 2 && bit32(s_leaf, Ua)) ? 0 : 1;   // pm:276-281
                 nrev = nl + notin + (msub == 1 ? 1 : 0);
             } else {
                 if (msub == 1) nrev = p;                                                   // :133-134
-                else {
-                    int nb = 0;
-                    for (int i = 0; i < nw32; ++i) nb += __popc(s_bnd[i]);
-                    nrev = nb + 2 - ((int)s_off[U + 1] - (int)s_off[U]);                   // pm:283-284
-                }
+                else nrev = nbnd + 2 - ((int)s_off[U + 1] - (int)s_off[U]);                // pm:283-284
             }
             const double log_q2 = -log((double)nfwd), log_q1 = -log((double)nrev);
             logq = log_q2 - log_q1;
         }
-        // ---- score + accept: one warp per proposal ---------------------------------------
-        for (int j = warp; j < nm; j += nw) {
-            const int U = s_mvU[j], Ua = s_mvUadj[j];
-            const u64 *Crow = Mc + (size_t)U * W;
-            const u64 *Arow = (Ua >= 0) ? Mc + (size_t)Ua * W : nullptr;
+        // ---- score + accept + apply, eight proposals per pass -----------------------------------
+        double log_p = 0.0;
+        for (int g0 = 0; g0 < nm; g0 += 8) {
+            const int mi = lane >> 2, q = lane & 3, j = g0 + mi;
+            const bool valid = j < nm;
+            int U = 0, Ua = -1;
+            if (valid) { U = s_mvU[j]; Ua = s_mvUadj[j]; }
+            const bool adj = Ua >= 0;
+            u64 Cw[WMAX], Aw[WMAX], X[WMAX];
             int kb = 0, ks = 0;
-            double sc[4] = {0.0, 0.0, 0.0, 0.0};
-            if (MODEL == PDG_MODEL_GGM) {
-                const int e = ggm_move_scores(P, ws, Crow, Arow, node, lane, kb, ks, sc);
-                if (e) errflag |= e;
-            } else {
-                for (int w = 0; w < W; ++w) {
-                    u64 b = Crow[w];
-                    if ((node >> 6) == w) b &= ~(1ull << (node & 63));
-                    kb += __popcll(b);
-                    if (Arow) ks += __popcll(b & Arow[w]);
-                }
-            }
-            if (lane == 0) {
-                const bool adj = Ua >= 0;
-                if (MODEL != PDG_MODEL_UNIFORM) {
-                    // algorithmic work of this proposal: the complete sets the reference scores
-                    const int ksz[4] = {kb, ks, kb + 1, adj ? ks + 1 : 0};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const unsigned long long kk_ = (unsigned long long)ksz[q];
-                        if (!kk_) continue;
-                        s_work[0] += 8ull * kk_ * kk_ * (P.dmode == 2 ? 2ull : 1ull);
-                        s_work[1] += (2ull * kk_ * kk_ * kk_ + 3ull * kk_ * kk_ + 6ull * kk_) * (P.dmode == 2 ? 2ull : 1ull);
-                        s_work[2] += 1ull; s_work[3] += kk_;
-                    }
-                }
+            for (int w = 0; w < WMAX; ++w) {
+                Cw[w] = (valid && w < W) ? Mc[(size_t)U * W + w] : 0ull;
+                Aw[w] = (valid && adj && w < W) ? Mc[(size_t)Ua * W + w] : 0ull;
+                const u64 vb = ((node >> 6) == w) ? (1ull << (node & 63)) : 0ull;
+                const u64 B = Cw[w] & ~vb, S0 = B & Aw[w];
+                kb += __popcll(B); ks += __popcll(S0);
+                X[w] = (q == 0) ? B : (q == 1) ? S0 : (q == 2) ? (B | vb) : (S0 | vb);
+            }
+            double sc = 0.0;
+            if (MODEL != PDG_MODEL_UNIFORM) {
+                const int kq = (q == 0) ? kb : (q == 1) ? ks : (q == 2) ? kb + 1 : ks + 1;
+                errflag |= warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, wk);
+            }
+            const double sc1 = __shfl_down_sync(PDG_FULL, sc, 1), sc2 = __shfl_down_sync(PDG_FULL, sc, 2),
+                         sc3 = __shfl_down_sync(PDG_FULL, sc, 3);
+            bool acc = false;
+            double delta = 0.0;
+            if (valid && q == 0) {
                 double log_p2, log_p1, log_g2, log_g1;
                 if (mtype == 0) {
                     const int cC = kb, cS = ks, cCn = kb + 1, cSn = adj ? ks + 1 : 0;
-                    log_p2 = sc[2] - (adj ? sc[3] : 0.0);
-                    log_p1 = sc[0] - sc[1];
+                    log_p2 = sc2 - (adj ? sc3 : 0.0);
+                    log_p1 = sc - sc1;
                     log_g2 = prior_partial(P, cCn, cSn, 0);
                     log_g1 = prior_partial(P, cC, cS, 1);
-                    if (msub == 0) { log_p1 += sc[3]; log_g1 += prior_partial(P, 1, cS, 1); }   // :261-263
+                    if (msub == 0) { log_p1 += sc3; log_g1 += prior_partial(P, 1, cS, 1); }   // :261-263
                 } else {
                     const int cC = kb + 1, cS = adj ? ks + 1 : 0, cCn = kb, cSn = ks;
-                    log_p2 = sc[0] - sc[1];
-                    log_p1 = sc[2] - (adj ? sc[3] : 0.0);
+                    log_p2 = sc - sc1;
+                    log_p1 = sc2 - (adj ? sc3 : 0.0);
                     log_g2 = prior_partial(P, cCn, cSn, 1);
                     log_g1 = prior_partial(P, cC, cS, 0);
-                    if (msub == 1) { log_p2 += sc[3]; log_g2 += prior_partial(P, 1, cSn, 1); }  // :293-295
+                    if (msub == 1) { log_p2 += sc3; log_g2 += prior_partial(P, 1, cSn, 1); }  // :293-295
                 }
                 const double dl = log_p2 - log_p1, dp = log_g2 - log_g1;
                 const double tot = (dl + dp) + logq;
@@ -265,56 +331,56 @@ __global__ void __launch_bounds__(128) k_mh_run(PdgParams P, long long it_begin,
                 if (R.on) u = R.mv_u[R.it_off[(size_t)chain * (R.n_samples + 1) + it] + j];
                 else u = draw_unif(P.seed_lo, P.seed_hi, gchain, (u32)it, TAG_MOVE, (u32)U);
                 const double e = exp(tot);
-                const bool acc = u <= (e < 1.0 ? e : 1.0);                                        // :268,:300
-                s_delta[j] = dl + dp; s_acc[j] = acc ? 1 : 0;
-                s_dl[j] = dl; s_dp[j] = dp; s_u[j] = u;
-            }
-        }
-        __syncthreads();
-        // ---- apply in proposal order: records, bit flips, running log-probability ---------
-        if (warp == 0) {
-            double log_p = 0.0;
-            for (int j = 0; j < nm; ++j) {
+                acc = u <= (e < 1.0 ? e : 1.0);                                                 // :268,:300
+                delta = dl + dp;
                 const long long kk = k + j + 1;
-                const int U = s_mvU[j], Ua = s_mvUadj[j];
-                if (P.mvlog_cap && lane == 0 && kk - 1 < P.mvlog_cap) {
+                if (P.mvlog_cap && kk - 1 < P.mvlog_cap) {
                     const size_t o = (size_t)chain * P.mvlog_cap + (kk - 1);
-                    P.ml_dlik[o] = s_dl[j]; P.ml_dprior[o] = s_dp[j]; P.ml_logq[o] = logq; P.ml_u[o] = s_u[j];
-                    P.ml_acc[o] = s_acc[j]; P.ml_U[o] = U;
+                    P.ml_dlik[o] = dl; P.ml_dprior[o] = dp; P.ml_logq[o] = logq; P.ml_u[o] = u;
+                    P.ml_acc[o] = acc ? 1 : 0; P.ml_U[o] = U;
                 }
-                if (!s_acc[j]) continue;
-                log_p += s_delta[j];
-                if (nrec < P.rec_cap) {
-                    const size_t ro = (size_t)chain * P.rec_cap + nrec;
-                    if (lane == 0) {
-                        pdg_update h;
-                        h.i = (int)it; h.k = (int)kk; h.node = (unsigned short)node; h.U = (unsigned short)U;
-                        h.Uadj = (short)Ua; h.type = (unsigned char)mtype; h.pad = 0;
-                        P.rec[ro] = h;
-                    }
-                    for (int w = lane; w < 2 * W; w += 32) {
-                        u64 v;
-                        if (w < W) v = Mc[(size_t)U * W + w];
-                        else v = (Ua >= 0) ? Mc[(size_t)Ua * W + (w - W)] : 0ull;
-                        P.rec_bits[ro * 2 * W + w] = v;
-                    }
-                } else errflag |= ERR_OVERFLOW;
-                ++nrec;
-                __syncwarp();
-                if (lane == 0) {                         // junction_tree.py:78-100 connect / disconnect
-                    Mc[(size_t)U * W + (node >> 6)] ^= 1ull << (node & 63);
-                    Nc[(size_t)node * W + (U >> 6)] ^= 1ull << (U & 63);
-                }
-                __syncwarp();
             }
-            logl_prev = logl_prev + log_p;               // :304 running sum
-            if (lane == 0) P.logl[(size_t)chain * P.n_samples + it] = logl_prev;
+            // accepted proposals in order: record append, running log-probability, bit flips
+            const u32 am = __ballot_sync(PDG_FULL, acc);
+            if (acc) {
+                const long long slot_r = nrec + __popc(am & lt);
+                if (slot_r < P.rec_cap) {
+                    const size_t ro = (size_t)chain * P.rec_cap + slot_r;
+                    pdg_update h;
+                    h.i = (int)it; h.k = (int)(k + j + 1); h.node = (unsigned short)node; h.U = (unsigned short)U;
+                    h.Uadj = (short)Ua; h.type = (unsigned char)mtype; h.pad = 0;
+                    P.rec[ro] = h;
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w) if (w < W) { P.rec_bits[ro * 2 * W + w] = Cw[w]; P.rec_bits[ro * 2 * W + W + w] = Aw[w]; }
+                } else errflag |= ERR_OVERFLOW;
+            }
+            u32 rem = am;
+            while (rem) {                                   // :269,:301 log_p += ... in proposal order
+                const int src = __ffs((int)rem) - 1;
+                rem &= rem - 1;
+                log_p += __shfl_sync(PDG_FULL, delta, src);
+            }
+            nrec += __popc(am);
+            __syncwarp();
+            if (acc) {                                      // junction_tree.py:78-100 connect / disconnect
+                atomicXor(&Mc[(size_t)U * W + (node >> 6)], 1ull << (node & 63));
+                atomicXor(&Nc[(size_t)node * W + (U >> 6)], 1ull << (U & 63));
+            }
+            __syncwarp();
         }
         k += nm;
-        __syncthreads();
+        logl_prev = logl_prev + log_p;                      // :304 running sum
+        if (lane == 0) P.logl[(size_t)chain * P.n_samples + it] = logl_prev;
     }
-    if (tid == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
     __syncwarp();
-    if (lane < 4 && s_work[2]) atomicAdd(&P.work[chain * 4 + lane], s_work[lane]);
+    if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
+    if (lane == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
+    // work counters are kept per lane: reduce over the warp, one atomic per counter
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        unsigned long long v = wk[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PDG_FULL, v, o);
+        if (lane == 0 && v) atomicAdd(&P.work[chain * 8 + q], v);
+    }
     if (errflag) atomicOr(&P.err[chain], errflag);
 }

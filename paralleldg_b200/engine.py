@@ -89,7 +89,7 @@ def bits_to_sets(bits):
 
 class _Scorer(object):
     def __init__(self, sd):
-        self.ctx = nat.Context(sd.p, 1, 1, rec_cap=0)
+        self.ctx = nat.Context(sd.p, 64, 1, rec_cap=0)      # 64 warp slots for the batch scorer
         configure_model(self.ctx, sd)
         self.W = self.ctx.W
 

@@ -1,0 +1,26 @@
+"""Developer timing probe: per-iteration time of the MH kernel for the uniform and GGM models."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from paralleldg_b200 import _native as nat, engine, datagen, mh_parallel as mh
+from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
+
+p, n, C, M, R = int(sys.argv[1]) if len(sys.argv) > 1 else 50, 100, 1024, 2000, 100
+X, _ = datagen.ggm_ar_data(p, n, 50)
+for name in sys.argv[2:] or ["uniform", "ggm"]:
+    if name == "uniform":
+        sd = seqdist.UniformJTDistribution(p)
+    else:
+        sd = seqdist.GGMJTPosterior(); sd.init_model(X, np.identity(p), 1.0, {})
+    ctx = engine.make_context(sd, mh.get_prior(["mbc", 2.0, 4.0]), C, M, seed=1, rec_cap=M)
+    for rep in range(2):
+        ctx.set_cliques(None); ctx.randomize(0)
+        ctx.enable_timing(True)
+        ctx.sample(0, R); ctx.sync()
+        tm = ctx.timing(); ctx.enable_timing(False)
+    nprop, nacc = ctx.counts()
+    print("%-8s p=%d run %.2f ms (%.2f us/iter)  randomize %.2f ms  prop/iter %.2f acc %.3f  -> %.1f Mprop/s" % (
+        name, p, tm["ms_run"], 1e3 * tm["ms_run"] / M, tm["ms_randomize"], nprop.mean() / M, nacc.sum() / nprop.sum(),
+        nprop.sum() / (tm["ms_run"] + tm["ms_randomize"]) / 1e3))
+    ctx.close()

@@ -142,6 +142,60 @@ def test_ggm_scorer_matches_reference():
         assert close(got, g["ggm_score_" + tag], 1e-10).all(), (tag, np.abs(got - g["ggm_score_" + tag]).max())
 
 
+def _loglin_sd(data, levels, alpha):
+    from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
+    sd = seqdist.LogLinearJTPosterior()
+    sd.init_model(np.asarray(data).astype(np.int64), alpha, [list(range(int(l))) for l in levels], {}, {})
+    return sd
+
+
+def test_loglin_scorer_matches_reference():
+    from paralleldg_b200 import engine
+    g = load_golden("scorers")
+    for tag in ("czech", "p15"):
+        for atag, alpha in (("a1", 1.0), ("a05", 0.5)):
+            sd = _loglin_sd(g["ll_%s_data" % tag], g["ll_%s_levels" % tag], alpha)
+            got = engine.scorer_for(sd).ctx.score_sets(g["ll_%s_sets" % tag])
+            want = g["ll_%s_score_%s" % (tag, atag)]
+            assert close(got, want, 1e-11).all(), (tag, atag, np.abs(got - want).max())
+    sd = _loglin_sd(g["ll_l3_data"], g["ll_l3_levels"], 2.0)
+    got = engine.scorer_for(sd).ctx.score_sets(g["ll_l3_sets"])
+    assert close(got, g["ll_l3_score_a2"], 1e-11).all()
+
+
+def test_loglin_sparse_cell_path_equals_dense(monkeypatch):
+    """sets with more cells than the dense per-warp table go through the hashed-cell pool"""
+    from paralleldg_b200 import engine
+    g = load_golden("scorers")
+    monkeypatch.setenv("PDG_HIST_CELLS", "8")
+    sd = _loglin_sd(g["ll_p15_data"], g["ll_p15_levels"], 1.0)
+    got = engine.scorer_for(sd).ctx.score_sets(g["ll_p15_sets"])
+    assert close(got, g["ll_p15_score_a1"], 1e-11).all(), np.abs(got - g["ll_p15_score_a1"]).max()
+    sd = _loglin_sd(g["ll_l3_data"], g["ll_l3_levels"], 2.0)
+    got = engine.scorer_for(sd).ctx.score_sets(g["ll_l3_sets"])
+    assert close(got, g["ll_l3_score_a2"], 1e-11).all()
+
+
+def test_memo_table_pressure_does_not_change_results(monkeypatch):
+    """a memo table far too small for the visited sets only costs recomputation"""
+    from tests import gpu_common as gc
+    from paralleldg_b200 import engine
+    g = load_golden("cfg2_ggm50_parallel_s1")
+    outs = []
+    for bits in ("8", "20"):
+        monkeypatch.setenv("PDG_MEMO_BITS", bits)
+        ctx = engine.make_context(gc.product_sd(g), gc.product_prior(g), 8, 600, seed=5, rec_cap=2400)
+        ctx.set_cliques(None)
+        ctx.randomize(0)
+        ctx.sample(0, 100)
+        ctx.sync()
+        outs.append((ctx.counts(), ctx.logl(), ctx.updates()))
+        ctx.close()
+    assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][0][1], outs[1][0][1])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2][1], outs[1][2][1])
+
+
 def test_no_cpu_fallback_for_unknown_plugins():
     from paralleldg_b200 import engine
 
