@@ -234,7 +234,7 @@ def main():
     # roofline of the dominant kernel (k_mh_run): algorithmic bytes / CUDA-event kernel time.
     # Unit = one complete set actually evaluated (memo misses); the sets the
     # proposals REQUESTED (4 per proposal, hits + misses) are reported next to it.
-    dw = {k_: work1[k_] - work0[k_] for k_ in work1}
+    dw = {k_: work1[k_] - work0[k_] for k_ in work1 if not isinstance(work1[k_], list)}
     peak, how = peaks()
     run_s = tm["ms_run"] * 1e-3
     ach = dw["bytes"] / run_s / 1e9 if run_s > 0 else 0.0

@@ -289,10 +289,10 @@ __device__ __forceinline__ int ggm_set_score(const PdgParams &P, const WarpScrat
 // LANE its own complete set and factorises it in REGISTERS: the packed lower triangle of
 // A[X, X] is gathered with fully unrolled, statically indexed code and reduced by a right-looking
 // LDL^T in ascending vertex order.  All lanes of the warp run the same straight-line code for
-// K = 4 or 8, whichever covers the warp-wide largest set; smaller sets are padded with identity rows,
+// K = 4, 8 or 12, whichever covers the warp-wide largest set; smaller sets are padded with identity rows,
 // which leaves every operation on the real block -- and therefore the result bit pattern --
 // unchanged, so score(X) stays a pure function of X.  32 scores per warp pass, no shared memory.
-#define PDG_KT 8                        // largest clique of the lane-private path
+#define PDG_KT 12                       // largest clique of the lane-private path
 
 struct LaneScratch { int unused; };
 
@@ -300,9 +300,19 @@ struct LaneScratch { int unused; };
 // two-pass loop, which keeps the hot loop small (the MH kernel is instruction-cache sensitive:
 // 32 KB L1.5 I-cache, several warps per SM at different program counters) and every array in
 // registers.
+#ifdef PDG_PHASE_TIMERS
+__device__ unsigned long long g_pt[8];
+#define LPT(i) { const long long n_ = clock64(); lp[i] += (unsigned long long)(n_ - l0); l0 = n_; }
+#else
+#define LPT(i)
+#endif
+
 template <int K, int WMAX>
 __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&X)[WMAX], int k, double &score)
 {
+#ifdef PDG_PHASE_TIMERS
+    long long l0 = clock64(); unsigned long long lp[5] = {0, 0, 0, 0, 0};
+#endif
     int idx[K];
     u64 Y[WMAX];
 #pragma unroll
@@ -317,6 +327,7 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
         }
         idx[t] = g;
     }
+    LPT(0)
     double ld[2] = {0.0, 0.0};
     bool ok = true;
     const int npass = (P.dmode == 2) ? 2 : 1;
@@ -335,6 +346,7 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
                 a[i * (i + 1) / 2 + l] = v;
             }
         }
+        LPT(1)
         double prod = 1.0, piv[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -350,6 +362,7 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
                 for (int l = j + 1; l <= i; ++l) a[i * (i + 1) / 2 + l] -= f * a[l * (l + 1) / 2 + j];
             }
         }
+        LPT(2)
         double v;
         if (prod > 1e-280 && prod < 1e280) v = log(prod);
         else {                               // product left the double range: sum the logs instead
@@ -358,12 +371,17 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
             for (int j = 0; j < K; ++j) v += log(piv[j]);
         }
         ld[pass] = v;
+        LPT(3)
     }
     if (P.dmode == 1) {
 #pragma unroll
         for (int j = 0; j < K; ++j) if (j < k) ld[1] += P.logDdiag[idx[j]];
     }
     score = ggm_score_from(P, k, ld[0], ld[1]);
+    LPT(4)
+#ifdef PDG_PHASE_TIMERS
+    if ((threadIdx.x & 31) == 0) { for (int q_ = 0; q_ < 5; ++q_) atomicAdd(&g_pt[q_], lp[q_]); atomicAdd(&g_pt[5 + (K == 8)], 1ull); }
+#endif
     return (ok || k == 0) ? 0 : ERR_NUMERIC;
 }
 
@@ -375,7 +393,8 @@ __device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const u64 (&X
     const int kmax = (int)__reduce_max_sync(PDG_FULL, (unsigned)k);
     if (kmax == 0) { score = 0.0; return 0; }
     if (kmax <= 4) return ggm_lane_score_k<4, WMAX>(P, X, k, score);
-    return ggm_lane_score_k<8, WMAX>(P, X, k, score);
+    if (kmax <= 8) return ggm_lane_score_k<8, WMAX>(P, X, k, score);
+    return ggm_lane_score_k<12, WMAX>(P, X, k, score);
 }
 
 template <int WMAX>

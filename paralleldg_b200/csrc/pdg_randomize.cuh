@@ -100,11 +100,12 @@ __global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long cha
     build_derived(P, chain_begin + c, threadIdx.x, s_off, s_fill);
 }
 
-__global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u32 iter)
+// randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
+// shared memory.  Works on the global-memory state and rebuilds N and the CSR at the end.
+__device__ __noinline__ void randomize_chain(const PdgParams &P, const RandScratch &Z, long long chain, u32 iter,
+                                             unsigned char *smem, int lane)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int p = P.p, W = P.W, lane = threadIdx.x;
-    const long long chain = blockIdx.x;
+    const int p = P.p, W = P.W;
     const RandSmem L = rand_smem_layout(p, W);
     unsigned short *card = (unsigned short *)(smem + L.off_card), *order = (unsigned short *)(smem + L.off_order);
     unsigned short *cliqueof = (unsigned short *)(smem + L.off_cliqueof), *keys = (unsigned short *)(smem + L.off_keys);
@@ -302,4 +303,10 @@ __global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u3
     __syncwarp();
     __threadfence_block();
     build_derived(P, chain, lane, s_off, fill);
+}
+
+__global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u32 iter)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    randomize_chain(P, Z, blockIdx.x, iter, smem, threadIdx.x);
 }

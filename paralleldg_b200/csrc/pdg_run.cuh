@@ -13,6 +13,21 @@
 #pragma once
 #include "pdg_kernels.cuh"
 #include "pdg_loglin.cuh"
+#include "pdg_randomize.cuh"
+
+// developer-only latency attribution: nvcc -DPDG_PHASE_TIMERS accumulates clock64() deltas of the
+// phases of an iteration into work[6] (phase id in the high bits is not needed: one run per phase
+// selection, chosen with the PDG_PHASE environment variable through P.mvlog_cap's sign bit... no:
+// simply eight counters in the per-chain `work` slots 8..15).
+#ifdef PDG_PHASE_TIMERS
+#define PT_DECL long long pt_last = clock64(); unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PT(i) { const long long pt_now = clock64(); pt[i] += (unsigned long long)(pt_now - pt_last); pt_last = pt_now; }
+#define PT_FLUSH if (lane == 0) for (int q_ = 0; q_ < 8; ++q_) atomicAdd(&P.work[chain * 16 + 8 + q_], pt[q_]);
+#else
+#define PT_DECL
+#define PT(i)
+#define PT_FLUSH
+#endif
 
 struct RunSmem {
     int off_tri, off_idx, off_sub, off_leaf, off_bnd, off_partner, off_mvU, off_mvUadj, off_csr_off, off_csr_adj,
@@ -112,7 +127,7 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
 
 template <int MODEL, int WMAX, bool SMEM_STATE>
 __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long it_begin, long long it_end,
-                                                PdgReplayDev R, int lockstep)
+                                                PdgReplayDev R, int lockstep, RandScratch Z, long long randomize, int smem_per_warp)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
     const int p = P.p, W = P.W;
@@ -120,7 +135,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     const long long chain = (long long)blockIdx.x * wpc + warp;
     if (chain >= P.n_chains) return;                       // (lockstep is only set when no warp exits here)
     const RunSmem L = run_smem_layout(p, W, SMEM_STATE);
-    unsigned char *smem = smem_all + (size_t)warp * L.total;
+    unsigned char *smem = smem_all + (size_t)warp * smem_per_warp;
     u64 *s_sub = (u64 *)(smem + L.off_sub);
     u32 *s_sub32 = (u32 *)(smem + L.off_sub);
     u32 *s_leaf = (u32 *)(smem + L.off_leaf);
@@ -156,11 +171,26 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
     const u32 lt = (1u << lane) - 1u;
     const int nw32 = (p + 31) >> 5;
+    PT_DECL
 
     for (long long it = it_begin; it < it_end; ++it) {
         // chains of one CTA start every iteration together: the loop body is larger than the
         // L1.5 instruction cache, in step the warps share its fetches instead of each streaming it
         if (lockstep) __syncthreads();
+        // ---- junction-tree randomisation every `randomize` iterations (mh_parallel.py:226-228),
+        // fused here so that a whole run is ONE launch and no chain ever waits for another.  The
+        // randomiser works on the global-memory state and reuses this warp's shared memory.
+        if (randomize > 0 && it % randomize == 0) {
+            __syncwarp();
+            if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
+            __syncwarp();
+            randomize_chain(P, Z, chain, (u32)it, smem, lane);
+            __syncwarp();
+            for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
+            for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
+            if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; }
+            __syncwarp();
+        }
         // ---- draws (mh_parallel.py:230-231) -------------------------------------------------
         int node, mtype, aux = -1;
         u32 r[4] = {0u, 0u, 0u, 0u};
@@ -177,6 +207,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
         int msub = 0;
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) if (w < W) msub += __popcll(s_sub[w]);
+        PT(0)
         if (msub == 0) mtype = 0;            // :237-240 forced move types
         if (msub == p) mtype = 1;
         const bool special = (mtype == 0 && msub == 0) || (mtype == 1 && msub <= 2);
@@ -209,6 +240,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             nm += __popc(fl);
         }
         __syncwarp();
+        PT(1)
         int nfwd = nm;
         double logq = 0.0;
         const u32 *set = (mtype == 0) ? s_bnd : s_leaf;
@@ -280,6 +312,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             const double log_q2 = -log((double)nfwd), log_q1 = -log((double)nrev);
             logq = log_q2 - log_q1;
         }
+        PT(2)
         // ---- score + accept + apply, eight proposals per pass -----------------------------------
         double log_p = 0.0;
         for (int g0 = 0; g0 < nm; g0 += 8) {
@@ -299,11 +332,13 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
                 kb += __popcll(B); ks += __popcll(S0);
                 X[w] = (q == 0) ? B : (q == 1) ? S0 : (q == 2) ? (B | vb) : (S0 | vb);
             }
+            PT(3)
             double sc = 0.0;
             if (MODEL != PDG_MODEL_UNIFORM) {
                 const int kq = (q == 0) ? kb : (q == 1) ? ks : (q == 2) ? kb + 1 : ks + 1;
                 errflag |= warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, wk);
             }
+            PT(4)
             const double sc1 = __shfl_down_sync(PDG_FULL, sc, 1), sc2 = __shfl_down_sync(PDG_FULL, sc, 2),
                          sc3 = __shfl_down_sync(PDG_FULL, sc, 3);
             bool acc = false;
@@ -340,6 +375,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
                     P.ml_acc[o] = acc ? 1 : 0; P.ml_U[o] = U;
                 }
             }
+            PT(5)
             // accepted proposals in order: record append, running log-probability, bit flips
             const u32 am = __ballot_sync(PDG_FULL, acc);
             if (acc) {
@@ -368,11 +404,13 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             }
             __syncwarp();
         }
+        PT(6)
         k += nm;
         logl_prev = logl_prev + log_p;                      // :304 running sum
         if (lane == 0) P.logl[(size_t)chain * P.n_samples + it] = logl_prev;
     }
     __syncwarp();
+    PT_FLUSH
     if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
     if (lane == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
     // work counters are kept per lane: reduce over the warp, one atomic per counter
@@ -380,7 +418,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     for (int q = 0; q < 6; ++q) {
         unsigned long long v = wk[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PDG_FULL, v, o);
-        if (lane == 0 && v) atomicAdd(&P.work[chain * 8 + q], v);
+        if (lane == 0 && v) atomicAdd(&P.work[chain * 16 + q], v);
     }
     if (errflag) atomicOr(&P.err[chain], errflag);
 }

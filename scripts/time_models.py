@@ -23,4 +23,8 @@ for name in sys.argv[2:] or ["uniform", "ggm"]:
     print("%-8s p=%d run %.2f ms (%.2f us/iter)  randomize %.2f ms  prop/iter %.2f acc %.3f  -> %.1f Mprop/s" % (
         name, p, tm["ms_run"], 1e3 * tm["ms_run"] / M, tm["ms_randomize"], nprop.mean() / M, nacc.sum() / nprop.sum(),
         nprop.sum() / (tm["ms_run"] + tm["ms_randomize"]) / 1e3))
+    ph = ctx.work()["phase"]
+    if sum(ph):
+        tot = float(sum(ph)); names = ["draw+sub", "scan", "movelist", "sets", "score", "delta+accept", "apply", "-"]
+        print("   phase cycles/iter/chain: " + "  ".join("%s %.0f" % (nm_, v / (2.0 * C * M)) for nm_, v in zip(names, ph)))
     ctx.close()
