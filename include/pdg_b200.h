@@ -161,6 +161,11 @@ int pdg_enable_timing(pdg_ctx *ctx, int on);
 int pdg_get_timing(pdg_ctx *ctx, double *ms_run, double *ms_randomize, int64_t *n_run, int64_t *n_randomize);
 int pdg_get_work(pdg_ctx *ctx, int64_t work[16]);
 
+/* page-locked host memory for the output buffers (logl traces and update records are hundreds of
+ * MB per run; pinned destinations make pdg_get_* a single DMA).  Not tied to a context. */
+int pdg_host_alloc(void **ptr, int64_t bytes);
+int pdg_host_free(void *ptr);
+
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pdg_launch_count(pdg_ctx *ctx);
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "pdg_set_cliques", "pdg_randomize", "pdg_init_logl", "pdg_run", "pdg_sample", "pdg_sync",
     "pdg_get_counts", "pdg_get_logl", "pdg_compact_updates", "pdg_get_updates", "pdg_enable_move_log",
     "pdg_get_move_log", "pdg_score_sets", "pdg_edge_tallies", "pdg_launch_count",
-    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed",
+    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed", "pdg_host_alloc", "pdg_host_free",
 ]
 
 
@@ -79,6 +79,8 @@ def lib():
         "pdg_get_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64)]),
         "pdg_get_work": (C.c_int, [vp, C.POINTER(i64)]),
         "pdg_set_seed": (C.c_int, [vp, u64, u32]),
+        "pdg_host_alloc": (C.c_int, [C.POINTER(vp), i64]),
+        "pdg_host_free": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -86,6 +88,44 @@ def lib():
         f.argtypes = args
     _LIB = L
     return L
+
+
+class PinnedPool(object):
+    """Caching allocator of page-locked host memory for the result arrays (the same idea as
+    torch's CachingHostAllocator, without torch): numpy arrays handed out here return their block
+    to the pool when they are garbage collected, so back-to-back runs reuse the pinned pages."""
+
+    def __init__(self):
+        self.free = {}          # rounded size -> [ptr]
+
+    @staticmethod
+    def _round(nbytes):
+        return max(4096, 1 << (int(nbytes) - 1).bit_length()) if nbytes > (1 << 20) else 1 << 20
+
+    def empty(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes == 0:
+            return np.empty(shape, dtype)
+        size = self._round(nbytes)
+        lst = self.free.get(size)
+        if lst:
+            ptr = lst.pop()
+        else:
+            p = C.c_void_p()
+            if lib().pdg_host_alloc(C.byref(p), size) != 0:
+                return np.empty(shape, dtype)          # pinning failed: pageable memory still works
+            ptr = p.value
+        buf = (C.c_char * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, size, ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def _release(self, size, ptr):
+        self.free.setdefault(size, []).append(ptr)
+
+
+PINNED = PinnedPool()
 
 
 def _p(a):
@@ -207,7 +247,7 @@ class Context(object):
         return a, b
 
     def logl(self, out=None):
-        out = np.empty((self.n_chains, self.n_samples), np.float64) if out is None else out
+        out = PINNED.empty((self.n_chains, self.n_samples), np.float64) if out is None else out
         self._ck(self.L.pdg_get_logl(self.h, _p(out)))
         return out
 
@@ -216,8 +256,8 @@ class Context(object):
         tot = C.c_int64(0)
         off = np.zeros(self.n_chains + 1, np.int64)
         self._ck(self.L.pdg_compact_updates(self.h, C.byref(tot), _p(off)))
-        rec = np.empty(tot.value, UPDATE_DTYPE)
-        bits = np.empty((tot.value, 2, self.W), np.uint64)
+        rec = PINNED.empty((tot.value,), UPDATE_DTYPE)
+        bits = PINNED.empty((tot.value, 2, self.W), np.uint64)
         self._ck(self.L.pdg_get_updates(self.h, _p(rec), _p(bits)))
         return off, rec, bits
 

@@ -220,6 +220,8 @@ struct pdg_ctx {
     pdg_update *d_packed = nullptr;
     u64 *d_packed_bits = nullptr;
     long long packed_total = -1, packed_cap = 0;
+    int *d_since = nullptr;               // edge-tally scratch, kept between calls
+    unsigned long long *d_tally = nullptr;
     // replay staging
     std::vector<void *> replay_tmp;
     // CUDA-event timing of the MH and randomisation launches
@@ -476,6 +478,7 @@ int pdg_destroy(pdg_ctx *ctx)
     if (ctx->d_logD) cudaFree(ctx->d_logD);
     if (ctx->d_gconst) cudaFree(ctx->d_gconst);
     for (void *v : ctx->model_owned) cudaFree(v);
+    if (ctx->d_since) { cudaFree(ctx->d_since); cudaFree(ctx->d_tally); }
     if (ctx->d_packed) cudaFree(ctx->d_packed);
     if (ctx->d_packed_bits) cudaFree(ctx->d_packed_bits);
     if (ctx->P.ml_dlik) { cudaFree(ctx->P.ml_dlik); cudaFree(ctx->P.ml_dprior); cudaFree(ctx->P.ml_logq); cudaFree(ctx->P.ml_u); cudaFree(ctx->P.ml_acc); cudaFree(ctx->P.ml_U); }
@@ -926,9 +929,11 @@ int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies)
     CK(cudaSetDevice(ctx->device));
     PdgParams &P = ctx->P;
     const size_t pp = (size_t)P.p * P.p;
-    int *since = nullptr; unsigned long long *d_t = nullptr;
-    CK(cudaMalloc((void **)&since, (size_t)P.n_chains * pp * sizeof(int)));
-    CK(cudaMalloc((void **)&d_t, pp * 8));
+    if (!ctx->d_since) {
+        CK(cudaMalloc((void **)&ctx->d_since, (size_t)P.n_chains * pp * sizeof(int)));
+        CK(cudaMalloc((void **)&ctx->d_tally, pp * 8));
+    }
+    int *since = ctx->d_since; unsigned long long *d_t = ctx->d_tally;
     CK(cudaMemsetAsync(d_t, 0, pp * 8, ctx->stream));
     k_edge_tallies<<<(unsigned)P.n_chains, 32, 0, ctx->stream>>>(P, since, burnin, d_t);
     ctx->launches++;
@@ -936,11 +941,25 @@ int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies)
     std::vector<long long> h(pp);
     CK(cudaMemcpyAsync(h.data(), d_t, pp * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(since); cudaFree(d_t);
     for (int a = 0; a < P.p; ++a)
         for (int b = a + 1; b < P.p; ++b) h[(size_t)b * P.p + a] = h[(size_t)a * P.p + b];
     CK(cudaMemcpy(tallies, h.data(), pp * 8, cudaMemcpyDefault));
     return PDG_OK;
+}
+
+int pdg_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return PDG_E_ARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes > 0 ? (size_t)bytes : 16, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? PDG_E_NOMEM : PDG_E_CUDA; }
+    return PDG_OK;
+}
+
+int pdg_host_free(void *ptr)
+{
+    if (!ptr) return PDG_E_ARG;
+    return cudaFreeHost(ptr) == cudaSuccess ? PDG_OK : PDG_E_CUDA;
 }
 
 int pdg_enable_timing(pdg_ctx *ctx, int on)
