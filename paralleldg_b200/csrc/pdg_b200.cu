@@ -214,7 +214,7 @@ struct pdg_ctx {
     int wmax = 1;                         // compile-time word count the kernels are dispatched on
     int wpc = 1;                          // warps (= chains) per CTA of the MH kernel
     bool smem_state = false;
-    int memo_bits = 20;
+    int memo_bits = 24;
     // compaction
     long long *d_offsets = nullptr;
     pdg_update *d_packed = nullptr;
@@ -407,6 +407,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     pdg_ctx *ctx = new pdg_ctx();
     ctx->device = device;
     if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) ctx->wpc = x; }
+    ctx->memo_bits = 24;                  // 16M slots: 256 MB for one-word keys (hit rate saturates at 2^23)
     if (const char *v = getenv("PDG_MEMO_BITS")) { const int x = atoi(v); if (x >= 8 && x <= 26) ctx->memo_bits = x; }
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PDG_E_CUDA; }
     PdgParams &P = ctx->P;
@@ -415,6 +416,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     P.model = PDG_MODEL_UNIFORM; P.prior = PDG_PRIOR_MBC; P.prior_a = 2.0; P.prior_b = 4.0;
     P.n_chains = n_chains; P.chain0 = chain0; P.seed_lo = (u32)seed; P.seed_hi = (u32)(seed >> 32);
     P.n_samples = n_samples; P.rec_cap = rec_cap;
+    P.memo_small = getenv("PDG_NO_MEMO_SMALL") ? 0 : 1;
     const size_t C = (size_t)n_chains, pw = (size_t)p * P.W;
     cudaError_t e = cudaSuccess;
 #define TRY(x) if (e == cudaSuccess) e = (x)

@@ -66,6 +66,7 @@ struct PdgParams {
     int hist_cells;
     LoglinSparse sp;
     MemoTable memo;
+    int memo_small;             // GGM: also memoise the sets of the lane-private path
     // outputs
     double *logl;               // [chain][n_samples]
     long long *kcount, *nrec;   // [chain]

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long cha
 
 // randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
 // shared memory.  Works on the global-memory state and rebuilds N and the CSR at the end.
-__device__ __noinline__ void randomize_chain(const PdgParams &P, const RandScratch &Z, long long chain, u32 iter,
+__device__ __forceinline__ void randomize_chain(const PdgParams &P, const RandScratch &Z, long long chain, u32 iter,
                                              unsigned char *smem, int lane)
 {
     const int p = P.p, W = P.W;

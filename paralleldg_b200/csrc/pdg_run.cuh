@@ -31,7 +31,7 @@
 
 struct RunSmem {
     int off_tri, off_idx, off_sub, off_leaf, off_bnd, off_partner, off_mvU, off_mvUadj, off_csr_off, off_csr_adj,
-        off_M, off_N, off_lidx, total;
+        off_M, off_N, off_T, off_lidx, total;
 };
 
 __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state)
@@ -45,6 +45,7 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state
     s.off_sub = o;      o += W * 8;
     s.off_M = o;        o += smem_state ? p * W * 8 : 0;
     s.off_N = o;        o += smem_state ? p * W * 8 : 0;
+    s.off_T = o;        o += smem_state ? p * W * 8 : 0;     // adjacency bit-matrix of the latent tree
     s.off_leaf = o;     o += (np32 * 4 + 15) / 16 * 16;
     s.off_bnd = o;      o += (np32 * 4 + 15) / 16 * 16;
     s.off_idx = o;      o += a2;
@@ -76,16 +77,24 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     for (int w = 0; w < WMAX; ++w) kq += __popcll(X[w]);
     if (need) { wk[4] += 1ull; wk[5] += (unsigned long long)kq; }
     if (MODEL == PDG_MODEL_GGM) {
+        // small sets: one parallel round trip to the memo table for every lane, then the lanes
+        // that missed factorise their own set in registers (K = largest MISSING set) and publish it
         const bool small = need && kq <= PDG_KT;
+        bool shit = false;
         double s_small = 0.0;
-        err |= ggm_lane_scores<WMAX>(P, X, small ? kq : 0, s_small);
-        if (small) {
-            score = s_small;
+        if (small && P.memo_small) shit = memo_lookup<WMAX>(P.memo, X, W, s_small);
+        const bool smiss = small && !shit;
+        double s_new = 0.0;
+        err |= ggm_lane_scores<WMAX>(P, X, smiss ? kq : 0, s_new);
+        if (smiss) {
+            s_small = s_new;
+            if (P.memo_small) memo_insert<WMAX>(P.memo, X, W, s_new);
             const unsigned long long kk = (unsigned long long)kq, dm = (P.dmode == 2 ? 2ull : 1ull);
             wk[0] += 8ull * kk * kk * dm;
             wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * dm;
             wk[2] += 1ull; wk[3] += kk;
         }
+        if (small) score = s_small;
         need = need && !small;
         __syncwarp();
     }
@@ -158,9 +167,17 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     u64 *Ng = P.N + (size_t)chain * p * W;
     u64 *Mc = SMEM_STATE ? (u64 *)(smem + L.off_M) : Mg;
     u64 *Nc = SMEM_STATE ? (u64 *)(smem + L.off_N) : Ng;
+    u64 *Tt = (u64 *)(smem + L.off_T);                      // only with SMEM_STATE
     for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
     for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
     if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; }
+    if (SMEM_STATE) {
+        __syncwarp();
+        for (int i = lane; i < p * W; i += 32) Tt[i] = 0ull;
+        __syncwarp();
+        for (int t = lane; t < p; t += 32)
+            for (int e = s_off[t]; e < s_off[t + 1]; ++e) { const int a = s_adj[e]; Tt[(size_t)t * W + (a >> 6)] |= 1ull << (a & 63); }
+    }
     __syncwarp();
 
     const u32 gchain = P.chain0 + (u32)chain;
@@ -189,6 +206,13 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
             for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
             if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; }
+        if (SMEM_STATE) {
+            __syncwarp();
+            for (int i = lane; i < p * W; i += 32) Tt[i] = 0ull;
+            __syncwarp();
+            for (int t = lane; t < p; t += 32)
+                for (int e = s_off[t]; e < s_off[t + 1]; ++e) { const int a = s_adj[e]; Tt[(size_t)t * W + (a >> 6)] |= 1ull << (a & 63); }
+        }
             __syncwarp();
         }
         // ---- draws (mh_parallel.py:230-231) -------------------------------------------------
@@ -221,9 +245,21 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             if (t < p) {
                 const int inT = bit32(s_sub32, t);
                 int cnt = 0;
-                for (int e = s_off[t]; e < s_off[t + 1]; ++e) {
-                    const int a = s_adj[e];
-                    if (bit32(s_sub32, a)) { ++cnt; last = a; }
+                if (SMEM_STATE) {
+                    // neighbours inside the subtree = adjacency row & subtree bitset
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w) {
+                        if (w < W) {
+                            const u64 x = Tt[(size_t)t * W + w] & s_sub[w];
+                            cnt += __popcll(x);
+                            if (x && last < 0) last = w * 64 + __ffsll((long long)x) - 1;
+                        }
+                    }
+                } else {
+                    for (int e = s_off[t]; e < s_off[t + 1]; ++e) {
+                        const int a = s_adj[e];
+                        if (bit32(s_sub32, a)) { ++cnt; last = a; }
+                    }
                 }
                 leaf = inT && cnt == 1;
                 bnd = !inT && cnt >= 1;

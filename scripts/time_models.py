@@ -6,7 +6,7 @@ import torch
 from paralleldg_b200 import _native as nat, engine, datagen, mh_parallel as mh
 from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
 
-p, n, C, M, R = int(sys.argv[1]) if len(sys.argv) > 1 else 50, 100, 1024, 2000, 100
+p, n, C, M, R = int(sys.argv[1]) if len(sys.argv) > 1 else 50, 100, 1024, int(os.environ.get("TM_M", "2000")), 100
 X, _ = datagen.ggm_ar_data(p, n, 50)
 for name in sys.argv[2:] or ["uniform", "ggm"]:
     if name == "uniform":
