@@ -242,8 +242,15 @@ def main():
         req_bytes = None
     else:
         req_bytes = dw["sum_k_requested"] * w["n"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and wname == DEFAULT_WORKLOAD:
+        with open(tpath) as f:
+            traffic = json.load(f)["k_mh_run"]["dram_bytes_per_launch"]      # from the committed ncu capture
+    n_launch = max(tm["n_run"], 1)
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": how, "kernel": "k_mh_run",
+                "traffic": traffic, "algorithmic_bytes_per_launch": dw["bytes"] / n_launch,
+                "launches_per_step": n_launch / max(args.steps, 1), "peak_source": how, "kernel": "k_mh_run",
                 "kernel_ms_per_step": tm["ms_run"] / max(args.steps, 1),
                 "randomize_ms_per_step": tm["ms_randomize"] / max(args.steps, 1),
                 "kernel_share_of_step": tm["ms_run"] / dev_ms if dev_ms else None,

@@ -28,6 +28,8 @@ def build_native(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if os.environ.get("PDG_LANE_SMEM"):
+        cmd.insert(1, "-DPDG_LANE_SMEM")
     if os.environ.get("PDG_PHASE_TIMERS"):
         cmd.insert(1, "-DPDG_PHASE_TIMERS")
     if verbose:

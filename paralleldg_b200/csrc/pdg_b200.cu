@@ -21,8 +21,13 @@ __host__ __device__ inline InitSmem init_smem_layout(int p, int W)
 {
     InitSmem s; int o = 0;
     const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
+#ifdef PDG_LANE_SMEM
+    s.off_tri = o; o += PDG_KTRI * 32 * 8;
+    s.off_lidx = o; o += PDG_KT * 32 * 2;
+#else
     s.off_tri = o; o += 528 * 8;
     s.off_lidx = o;
+#endif
     s.off_sc = o; o += p * 8;
     s.off_ss = o; o += p * 8;
     s.off_idx = o; o += a2;
@@ -66,6 +71,8 @@ __global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
     ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
     LaneScratch ls;
     ls.unused = 0;
+    ls.a = (double *)(smem + L.off_tri);
+    ls.idx = (unsigned short *)(smem + L.off_lidx);
     const u64 *Mc = P.M + (size_t)chain * p * W;
     const int *E = P.edges + (size_t)chain * 2 * (p - 1);
     int errflag = 0;
@@ -142,7 +149,14 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     LaneScratch ls;
     ws.tri32 = (double *)smem;
     ls.unused = 0;
+#ifdef PDG_LANE_SMEM
+    ls.a = (double *)smem;
+    ls.idx = (unsigned short *)(smem + PDG_KTRI * 32 * 8);
+    ws.idx = (short *)(smem + PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2);
+#else
+    ls.a = nullptr; ls.idx = nullptr;
     ws.idx = (short *)(smem + 528 * 8);
+#endif
     ws.kbig = P.kbig;
     const int slot = blockIdx.x;
     ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
@@ -212,7 +226,7 @@ struct pdg_ctx {
     double *d_A = nullptr, *d_D = nullptr, *d_logD = nullptr, *d_gconst = nullptr;
     std::vector<void *> model_owned;      // log-linear buffers, freed on re-set / destroy
     int wmax = 1;                         // compile-time word count the kernels are dispatched on
-    int wpc = 1;                          // warps (= chains) per CTA of the MH kernel
+    int wpc = 8;                          // warps (= chains) per CTA of the MH kernel (8 -> one CTA per SM at 1024 chains)
     bool smem_state = false;
     int memo_bits = 24;
     // compaction
@@ -282,7 +296,13 @@ static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const 
     if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS>, sm))) return rc;
     const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
     time_begin(ctx, ctx->ev_run);
-    const int lockstep = (wpc > 1 && (long long)grid * wpc == ctx->P.n_chains && !getenv("PDG_NO_LOCKSTEP")) ? 1 : 0;
+    // chains of one CTA re-align every `lockstep` iterations (power of two, 0 = never)
+    int lockstep = 0;
+    if (wpc > 1 && (long long)grid * wpc == ctx->P.n_chains) {
+        lockstep = 16;
+        if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
+        if (lockstep & (lockstep - 1)) lockstep = 0;
+    }
     k_mh_run<MODEL, WMAX, SS><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
     time_end(ctx, ctx->ev_run);
     ctx->launches++;
@@ -345,7 +365,11 @@ template <int MODEL, int WMAX>
 static int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
 {
     long long grid = n_sets < ctx->P.n_chains ? n_sets : ctx->P.n_chains;
+#ifdef PDG_LANE_SMEM
+    const int sm = PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+#else
     const int sm = 528 * 8 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+#endif
     k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -406,6 +430,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     if (device < 0 || device >= ndev) return PDG_E_ARG;
     pdg_ctx *ctx = new pdg_ctx();
     ctx->device = device;
+    ctx->wpc = (n_chains % 8 == 0) ? 8 : (n_chains % 4 == 0) ? 4 : 1;
     if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) ctx->wpc = x; }
     ctx->memo_bits = 24;                  // 16M slots: 256 MB for one-word keys (hit rate saturates at 2^23)
     if (const char *v = getenv("PDG_MEMO_BITS")) { const int x = atoi(v); if (x >= 8 && x <= 26) ctx->memo_bits = x; }

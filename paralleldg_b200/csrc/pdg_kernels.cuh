@@ -295,7 +295,61 @@ __device__ __forceinline__ int ggm_set_score(const PdgParams &P, const WarpScrat
 // unchanged, so score(X) stays a pure function of X.  32 scores per warp pass, no shared memory.
 #define PDG_KT 12                       // largest clique of the lane-private path
 
-struct LaneScratch { int unused; };
+#define PDG_KTRI (PDG_KT * (PDG_KT + 1) / 2)
+struct LaneScratch {
+    int unused;
+    double *a;                          // [PDG_KTRI][32] lane-interleaved triangles (PDG_LANE_SMEM build)
+    unsigned short *idx;                // [PDG_KT][32]
+};
+
+// compact alternative (-DPDG_LANE_SMEM): the same ascending-order LDL^T with rolled loops over a
+// lane-private triangle in shared memory; ~10x fewer instructions of CODE than the unrolled
+// register variants (the MH kernel is instruction-fetch bound), more instructions EXECUTED.
+template <int WMAX>
+__device__ __forceinline__ int ggm_lane_score_smem(const PdgParams &P, const LaneScratch &ls, int lane, const u64 (&X)[WMAX],
+                                                   int k, double &score)
+{
+    if (k == 0) { score = 0.0; return 0; }
+    double *a = ls.a + lane;
+    unsigned short *idx = ls.idx + lane;
+    {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) {
+            u64 x = X[w];
+            while (x) { idx[t * 32] = (unsigned short)(w * 64 + __ffsll((long long)x) - 1); x &= x - 1; ++t; }
+        }
+    }
+    double ld[2] = {0.0, 0.0};
+    bool ok = true;
+    const int npass = (P.dmode == 2) ? 2 : 1, p = P.p;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+        const double *__restrict__ mat = pass ? P.Dm : P.A;
+        for (int i = 0, e = 0; i < k; ++i) {
+            const double *row = mat + (size_t)idx[i * 32] * p;
+            for (int l = 0; l <= i; ++l, ++e) a[e * 32] = __ldg(row + idx[l * 32]);
+        }
+        double prod = 1.0, lacc = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const int jj = (j * (j + 1)) >> 1;
+            const double d = a[(jj + j) * 32];
+            ok = ok && (d > 0.0);
+            prod *= d;
+            if (prod > 1e150 || prod < 1e-150) { lacc += log(prod); prod = 1.0; }
+            const double inv = 1.0 / d;
+            for (int i = j + 1; i < k; ++i) {
+                double *ri = a + ((i * (i + 1)) >> 1) * 32;
+                const double f = ri[j * 32] * inv;
+                for (int l = j + 1; l <= i; ++l) ri[l * 32] -= f * a[(((l * (l + 1)) >> 1) + j) * 32];
+            }
+        }
+        ld[pass] = lacc + log(prod);
+    }
+    if (P.dmode == 1) for (int j = 0; j < k; ++j) ld[1] += P.logDdiag[idx[j * 32]];
+    score = ggm_score_from(P, k, ld[0], ld[1]);
+    return ok ? 0 : ERR_NUMERIC;
+}
 
 // One inlined copy per K: the (rare) general-D case reuses the same code through a rolled
 // two-pass loop, which keeps the hot loop small (the MH kernel is instruction-cache sensitive:
@@ -389,8 +443,12 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
 // scores of the lanes' own sets; k = |X| for lanes that need one (<= PDG_KT), 0 for the others.
 // Warp-uniform dispatch on the largest k.
 template <int WMAX>
-__device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const u64 (&X)[WMAX], int k, double &score)
+__device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const LaneScratch &ls, int lane, const u64 (&X)[WMAX],
+                                               int k, double &score)
 {
+#ifdef PDG_LANE_SMEM
+    return ggm_lane_score_smem<WMAX>(P, ls, lane, X, k, score);
+#endif
     const int kmax = (int)__reduce_max_sync(PDG_FULL, (unsigned)k);
     if (kmax == 0) { score = 0.0; return 0; }
     if (kmax <= 4) return ggm_lane_score_k<4, WMAX>(P, X, k, score);
