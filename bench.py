@@ -259,6 +259,7 @@ def main():
                 "sets_evaluated_per_step": dw["sets"] / max(args.steps, 1),
                 "sets_requested_per_step": dw["sets_requested"] / max(args.steps, 1),
                 "memo_hit_rate": 1.0 - dw["sets"] / float(max(dw["sets_requested"], 1)),
+                "sets_hashed_cells_per_step": dw.get("sets_sparse", 0) / max(args.steps, 1),
                 "mean_set_size_requested": dw["sum_k_requested"] / float(max(dw["sets_requested"], 1)),
                 "mean_set_size_evaluated": dw["sum_k"] / float(max(dw["sets"], 1)),
                 "note": "latency/issue-bound integer kernel: scores come from the device-wide memo table, "

@@ -298,7 +298,9 @@ static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const 
     time_begin(ctx, ctx->ev_run);
     // chains of one CTA re-align every `lockstep` iterations (power of two, 0 = never)
     int lockstep = 0;
-    if (wpc > 1 && (long long)grid * wpc == ctx->P.n_chains) {
+    // (not for log-linear models with many rows: a table scan then costs ~100x an iteration and the
+    // other chains of the CTA must not wait for it)
+    if (wpc > 1 && (long long)grid * wpc == ctx->P.n_chains && !(MODEL == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192)) {
         lockstep = 16;
         if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
         if (lockstep & (lockstep - 1)) lockstep = 0;
