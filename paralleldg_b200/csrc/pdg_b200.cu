@@ -434,7 +434,9 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     ctx->device = device;
     ctx->wpc = (n_chains % 8 == 0) ? 8 : (n_chains % 4 == 0) ? 4 : 1;
     if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) ctx->wpc = x; }
-    ctx->memo_bits = 24;                  // 16M slots: 256 MB for one-word keys (hit rate saturates at 2^23)
+    // 16M slots (256 MB) for one- and two-word keys: the p = 50 hit rate saturates at 2^23; wider
+    // keys come with far more distinct cliques (p = 500: 21M per run), 32M slots = 2.7 GB there
+    ctx->memo_bits = (p > 128) ? 25 : 24;
     if (const char *v = getenv("PDG_MEMO_BITS")) { const int x = atoi(v); if (x >= 8 && x <= 26) ctx->memo_bits = x; }
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PDG_E_CUDA; }
     PdgParams &P = ctx->P;
@@ -650,7 +652,7 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
 
 static int launch_derived(pdg_ctx *ctx, long long b, long long n)
 {
-    const int sm = (2 * (ctx->P.p + 2)) * 2 + 64;
+    const int sm = (ctx->P.p + 2) * 4 + 64;
     k_build_derived<<<(unsigned)n, 32, sm, ctx->stream>>>(ctx->P, b, n);
     ctx->launches++;
     CK(cudaGetLastError());

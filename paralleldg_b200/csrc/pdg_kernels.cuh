@@ -156,11 +156,15 @@ __device__ __forceinline__ bool memo_lookup(const MemoTable &T, const u64 (&X)[W
             const u64 t = __ldcg(&T.tag[h]);
             if (t == 0ull) return false;
             if (t == tag) {
+                // key words and value in flight together: one round trip, not W + 1
+                u64 kw[WMAX];
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) kw[w] = (w < W) ? __ldcg(&T.keyw[(size_t)h * W + w]) : 0ull;
+                const u64 v = __ldcg(&T.val[h]);
                 bool same = true;
 #pragma unroll
-                for (int w = 0; w < WMAX; ++w) if (w < W) same = same && (__ldcg(&T.keyw[(size_t)h * W + w]) == X[w]);
+                for (int w = 0; w < WMAX; ++w) same = same && (kw[w] == X[w]);
                 if (same) {
-                    const u64 v = __ldcg(&T.val[h]);
                     if (v == MEMO_SENT) return false;
                     val = __longlong_as_double((long long)v);
                     return true;
@@ -369,18 +373,23 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
     long long l0 = clock64(); unsigned long long lp[5] = {0, 0, 0, 0, 0};
 #endif
     int idx[K];
-    u64 Y[WMAX];
+    if (WMAX == 1) {
+        u64 y = X[0];
 #pragma unroll
-    for (int w = 0; w < WMAX; ++w) Y[w] = X[w];
-#pragma unroll
-    for (int t = 0; t < K; ++t) {
-        int g = 0;
-        bool found = false;
+        for (int t = 0; t < K; ++t) { idx[t] = y ? __ffsll((long long)y) - 1 : 0; y &= y - 1; }
+    } else {
+        // multi-word keys: walk the words once with a dynamic counter into a small lane-private
+        // stack array (local memory, L1 resident), then read it back with static indices
+        int stk[K];
+        int t = 0;
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) {
-            if (!found && Y[w]) { g = w * 64 + __ffsll((long long)Y[w]) - 1; Y[w] &= Y[w] - 1; found = true; }
+            u64 y = X[w];
+            while (y && t < K) { stk[t++] = w * 64 + __ffsll((long long)y) - 1; y &= y - 1; }
         }
-        idx[t] = g;
+        for (; t < K; ++t) stk[t] = 0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) idx[q] = stk[q];
     }
     LPT(0)
     double ld[2] = {0.0, 0.0};

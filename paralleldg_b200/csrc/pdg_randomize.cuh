@@ -10,7 +10,7 @@
 struct RandSmem {
     int off_card, off_order, off_cliqueof, off_parent, off_keys, off_jdraw, off_comp, off_nodes, off_rank,
         off_cstart, off_canon, off_compidx, off_vind, off_wj, off_cnt, off_fill, off_off, off_newe,
-        off_done, off_inT, off_inw, off_isroot, off_numbered, off_used, off_X, total;
+        off_done, off_inT, off_inw, off_isroot, off_numbered, off_used, off_X, off_wmask, off_sepsz, off_deg32, total;
 };
 
 __host__ __device__ inline RandSmem rand_smem_layout(int p, int W)
@@ -26,6 +26,8 @@ __host__ __device__ inline RandSmem rand_smem_layout(int p, int W)
     s.off_fill = o; o += a2;   s.off_off = o; o += a2;    s.off_newe = o; o += 2 * a2;
     s.off_done = o; o += a1;   s.off_inT = o; o += a1;    s.off_inw = o; o += a1;  s.off_isroot = o; o += a1;
     s.off_numbered = o; o += W * 8; s.off_used = o; o += W * 8; s.off_X = o; o += W * 8;
+    s.off_wmask = o; o += a1; s.off_sepsz = o; o += a2;
+    s.off_deg32 = o; o += ((p + 2) * 4 + 15) / 16 * 16;
     s.total = o;
     return s;
 }
@@ -39,22 +41,31 @@ __device__ __forceinline__ bool subset_w(const u64 *a, const u64 *b, int W)
     for (int w = 0; w < W; ++w) if (a[w] & ~b[w]) return false;
     return true;
 }
+// the same over the word range [lo, hi] that holds all bits of a
+__device__ __forceinline__ bool subset_r(const u64 *a, const u64 *b, int lo, int hi)
+{
+    for (int w = lo; w <= hi; ++w) if (a[w] & ~b[w]) return false;
+    return true;
+}
 __device__ __forceinline__ bool equal_w(const u64 *a, const u64 *b, int W)
 {
     for (int w = 0; w < W; ++w) if (a[w] != b[w]) return false;
     return true;
 }
 
-// derived state of one chain: N = transpose of M, CSR of the tree.  Called by one warp.
-__device__ __forceinline__ void build_derived(const PdgParams &P, long long chain, int lane,
-                                              unsigned short *s_off, unsigned short *s_fill)
+// derived state of one chain: N = transpose of M, CSR of the tree.  Called by one warp; s_deg is
+// (p + 1) ints of shared memory.  O(p) per chain: degrees and fill cursors through shared atomics
+// over the edge list (the order inside an adjacency list carries no meaning).
+__device__ __forceinline__ void build_derived(const PdgParams &P, long long chain, int lane, int *s_deg)
 {
     const int p = P.p, W = P.W;
     u64 *Mc = P.M + (size_t)chain * p * W;
     u64 *Nc = P.N + (size_t)chain * p * W;
     const int *E = P.edges + (size_t)chain * 2 * (p - 1);
+    unsigned short *g_off = P.csr_off + (size_t)chain * (p + 1);
+    unsigned short *g_adj = P.csr_adj + (size_t)chain * 2 * p;
     for (int i = lane; i < p * W; i += 32) Nc[i] = 0ull;
-    for (int i = lane; i <= p; i += 32) { s_off[i] = 0; s_fill[i] = 0; }
+    for (int i = lane; i <= p; i += 32) s_deg[i] = 0;
     __syncwarp();
     for (int i = lane; i < p * W; i += 32) {
         const int t = i / W, w = i - t * W;
@@ -66,26 +77,25 @@ __device__ __forceinline__ void build_derived(const PdgParams &P, long long chai
             atomicOr(&Nc[(size_t)g * W + (t >> 6)], 1ull << (t & 63));
         }
     }
-    // degree histogram through 32-bit shared atomics on packed halves is awkward; the tree is
-    // tiny, so count with per-lane passes over the edge list instead
-    for (int t = lane; t < p; t += 32) {
-        int d = 0;
-        for (int e = 0; e < p - 1; ++e) d += (E[2 * e] == t) + (E[2 * e + 1] == t);
-        s_fill[t] = (unsigned short)d;
+    for (int e = lane; e < p - 1; e += 32) { atomicAdd(&s_deg[E[2 * e]], 1); atomicAdd(&s_deg[E[2 * e + 1]], 1); }
+    __syncwarp();
+    // exclusive prefix over p degrees: 32 per pass with a warp scan
+    int carry = 0;
+    for (int base = 0; base <= p; base += 32) {
+        const int t = base + lane;
+        const int d = (t < p) ? s_deg[t] : 0;
+        int incl = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(PDG_FULL, incl, o); if (lane >= o) incl += v; }
+        const int excl = carry + incl - d;
+        if (t <= p) { g_off[t] = (unsigned short)excl; if (t < p) s_deg[t] = excl; }
+        carry += __shfl_sync(PDG_FULL, incl, 31);
     }
     __syncwarp();
-    if (lane == 0) { int acc = 0; for (int t = 0; t < p; ++t) { s_off[t] = (unsigned short)acc; acc += s_fill[t]; } s_off[p] = (unsigned short)acc; }
-    __syncwarp();
-    unsigned short *g_off = P.csr_off + (size_t)chain * (p + 1);
-    unsigned short *g_adj = P.csr_adj + (size_t)chain * 2 * p;
-    for (int t = lane; t <= p; t += 32) g_off[t] = s_off[t];
-    for (int t = lane; t < p; t += 32) {
-        int o = s_off[t];
-        for (int e = 0; e < p - 1; ++e) {
-            const int a = E[2 * e], b = E[2 * e + 1];
-            if (a == t) g_adj[o++] = (unsigned short)b;
-            else if (b == t) g_adj[o++] = (unsigned short)a;
-        }
+    for (int e = lane; e < p - 1; e += 32) {
+        const int a = E[2 * e], b = E[2 * e + 1];
+        g_adj[atomicAdd(&s_deg[a], 1)] = (unsigned short)b;
+        g_adj[atomicAdd(&s_deg[b], 1)] = (unsigned short)a;
     }
     __syncwarp();
 }
@@ -95,9 +105,7 @@ __global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long cha
     extern __shared__ __align__(16) unsigned char smem[];
     const long long c = blockIdx.x;
     if (c >= chain_count) return;
-    unsigned short *s_off = (unsigned short *)smem;
-    unsigned short *s_fill = s_off + (P.p + 2);
-    build_derived(P, chain_begin + c, threadIdx.x, s_off, s_fill);
+    build_derived(P, chain_begin + c, threadIdx.x, (int *)smem);
 }
 
 // randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
@@ -115,10 +123,12 @@ __device__ __forceinline__ void randomize_chain(const PdgParams &P, const RandSc
     unsigned short *cstart = (unsigned short *)(smem + L.off_cstart), *canon = (unsigned short *)(smem + L.off_canon);
     unsigned short *compidx = (unsigned short *)(smem + L.off_compidx), *vind = (unsigned short *)(smem + L.off_vind);
     unsigned short *wj = (unsigned short *)(smem + L.off_wj), *cnt = (unsigned short *)(smem + L.off_cnt);
-    unsigned short *fill = (unsigned short *)(smem + L.off_fill), *s_off = (unsigned short *)(smem + L.off_off);
+    unsigned short *fill = (unsigned short *)(smem + L.off_fill);
     unsigned short *newe = (unsigned short *)(smem + L.off_newe);
     unsigned char *done = smem + L.off_done, *inT = smem + L.off_inT, *inw = smem + L.off_inw, *isroot = smem + L.off_isroot;
     u64 *numbered = (u64 *)(smem + L.off_numbered), *used = (u64 *)(smem + L.off_used), *X = (u64 *)(smem + L.off_X);
+    unsigned char *wmask = smem + L.off_wmask;
+    unsigned short *sepsz = (unsigned short *)(smem + L.off_sepsz);
     u64 *Mc = P.M + (size_t)chain * p * W;
     const u64 *Nc = P.N + (size_t)chain * p * W;
     u64 *adj = Z.adj + (size_t)chain * p * W, *K = Z.K + (size_t)chain * p * W, *sep = Z.sep + (size_t)chain * p * W;
@@ -190,22 +200,35 @@ __device__ __forceinline__ void randomize_chain(const PdgParams &P, const RandSc
         __syncwarp();
     }
 
+    // per clique: which words are non-empty (W <= 8 -> one byte) and the separator size, in shared
+    // memory, so that the per-separator scans below reject almost every clique without a global load
+    for (int d = lane; d < S; d += 32) {
+        unsigned int m = 0u; int sz = 0;
+        for (int w = 0; w < W; ++w) { if (K[(size_t)d * W + w]) m |= 1u << w; sz += __popcll(sep[(size_t)d * W + w]); }
+        wmask[d] = (unsigned char)m; sepsz[d] = (unsigned short)sz;
+    }
+    __syncwarp();
     // ---- (c) every distinct separator: components of the induced forest + generalised Pruefer
     int ne = 0;
     for (int c = 1; c < S; ++c) {
         if (done[c]) continue;           // warp-uniform (shared memory)
         if (lane < W) X[lane] = sep[(size_t)c * W + lane];
         __syncwarp();
+        // cliques of an AR-like graph are local: the separator's bits sit in one or two words
+        int wlo = W, whi = -1, xsz = 0;
+        unsigned int xm = 0u;
+        for (int w = 0; w < W; ++w) if (X[w]) { if (wlo == W) wlo = w; whi = w; xm |= 1u << w; xsz += __popcll(X[w]); }
         int P_ = 0, q = 0;
         for (int base = 0; base < S; base += 32) {
             const int d = base + lane;
             bool in = false, root = false, dn = false;
             if (d < S) {
-                in = subset_w(X, K + (size_t)d * W, W);
+                in = ((wmask[d] & xm) == xm) && subset_r(X, K + (size_t)d * W, wlo, whi);
                 if (in) {
                     const int pd = parent[d];
-                    const bool top = (pd < 0) || !subset_w(X, K + (size_t)pd * W, W);
-                    const bool eq = (d > 0) && equal_w(sep + (size_t)d * W, X, W);
+                    const bool top = (pd < 0) || ((wmask[pd] & xm) != xm) || !subset_r(X, K + (size_t)pd * W, wlo, whi);
+                    // sep[d] == X  <=>  same size and X inside sep[d]
+                    const bool eq = (d > 0) && sepsz[d] == xsz && subset_r(X, sep + (size_t)d * W, wlo, whi);
                     root = top || eq;
                     dn = !top && eq;
                 }
@@ -302,7 +325,7 @@ __device__ __forceinline__ void randomize_chain(const PdgParams &P, const RandSc
     }
     __syncwarp();
     __threadfence_block();
-    build_derived(P, chain, lane, s_off, fill);
+    build_derived(P, chain, lane, (int *)(smem + L.off_deg32));
 }
 
 __global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u32 iter)
