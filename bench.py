@@ -268,6 +268,7 @@ def main():
 
     # ------------------------------------------------------------------ end-to-end arm
     e2e = None
+    ess_info = {}
     if not args.no_e2e:
         h2d = 0
         if w["model"] == "ggm":
@@ -297,11 +298,25 @@ def main():
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
             dist.all_reduce(ep, op=dist.ReduceOp.SUM)
+        # edge-marginal ESS (second half of the metric) on a sample of chains, outside the timed region
+        try:
+            from paralleldg_b200 import ess as esslib
+            sample = list(range(0, C, max(1, C // 16)))[:16]
+            burn = M // 5
+            per_chain = esslib.batch_edge_ess(batch.offsets, batch.records, batch.bits, w["p"], M, sample, burnin=burn)
+            per_chain = per_chain[np.isfinite(per_chain)]
+            ess_info = {"edge_ess_per_chain_mean": float(per_chain.mean()) if len(per_chain) else None,
+                        "chains_sampled": len(sample), "burnin": burn,
+                        "definition": "median over edges with marginal in (0.05,0.95) of N/(1+2 sum rho_h), Geyer truncation"}
+        except Exception as ex:       # the estimator must never break the timing line
+            ess_info = {"error": repr(ex)}
         e2e = {"value": float(ep.item()) / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(et.item()) / max(args.steps, 1),
                "api": "paralleldg_b200.mh_parallel.sample_chains (host numpy in, host numpy out: logl traces, "
                       "compacted update records, final states, edge tallies)"}
 
+    if e2e is not None and ess_info.get("edge_ess_per_chain_mean"):
+        ess_info["ess_per_sec"] = ess_info["edge_ess_per_chain_mean"] * C * world / (e2e["ms_per_step"] * 1e-3)
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -319,6 +334,24 @@ def main():
         t = time.perf_counter()
         o = orc.run_many(m, orc.KIND_PARALLEL, sc, M, R, seed=8, n_threads=threads)
         dt = time.perf_counter() - t
+        try:
+            from paralleldg_b200 import ess as esslib
+            nc = min(sc, 16)
+            oe = orc.run_many(m, orc.KIND_PARALLEL, nc, M, R, seed=8, n_threads=threads, rec_cap=4 * M)
+            per = []
+            for c in range(nc):
+                na = int(oe["n_acc"][c])
+                rec = np.zeros(na, nat.UPDATE_DTYPE)
+                for f in ("i", "type", "node"):
+                    rec[f] = oe["recs"][c][:na][f]
+                v, cnt = esslib.chain_edge_ess(rec, oe["rec_bits"][c][:na], np.zeros((w["p"], w["p"]), np.uint8), M, burnin=M // 5)
+                if np.isfinite(v):
+                    per.append(v)
+            if per:
+                ess_info["cpu_ess_per_sec"] = float(np.mean(per)) * sc / dt
+                ess_info["cpu_edge_ess_per_chain_mean"] = float(np.mean(per))
+        except Exception as ex:
+            ess_info["cpu_error"] = repr(ex)
         cpu = {"value": float(o["n_prop"].sum() / dt), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d of %d chains x %d iterations, oracle/pdg_oracle.c (C port of the reference), %d threads"
                          % (sc, C, M, threads)}
@@ -333,7 +366,7 @@ def main():
                            "proposals_per_step_per_gpu": props_per_step,
                            "l2": "flushed between timed steps (256 MB write)"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "ess": ess_info}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
