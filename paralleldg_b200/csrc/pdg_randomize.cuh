@@ -56,7 +56,8 @@ __device__ __forceinline__ bool equal_w(const u64 *a, const u64 *b, int W)
 // derived state of one chain: N = transpose of M, CSR of the tree.  Called by one warp; s_deg is
 // (p + 1) ints of shared memory.  O(p) per chain: degrees and fill cursors through shared atomics
 // over the edge list (the order inside an adjacency list carries no meaning).
-__device__ __forceinline__ void build_derived(const PdgParams &P, long long chain, int lane, int *s_deg)
+template <typename PT>
+__device__ __forceinline__ void build_derived(const PT &P, long long chain, int lane, int *s_deg)
 {
     const int p = P.p, W = P.W;
     u64 *Mc = P.M + (size_t)chain * p * W;
@@ -108,9 +109,28 @@ __global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long cha
     build_derived(P, chain_begin + c, threadIdx.x, (int *)smem);
 }
 
+// The fields of PdgParams the randomiser needs, passed BY VALUE: randomize_chain is out of line (it
+// is cold inside the MH kernel and would bloat its loop body) and taking the address of the kernel
+// parameter block would force the whole block into local memory.
+struct RandArgs {
+    int p, W;
+    u64 *M, *N;
+    int *edges;
+    unsigned short *csr_off, *csr_adj;
+    int *err;
+    u32 chain0, seed_lo, seed_hi;
+};
+__device__ __forceinline__ RandArgs rand_args(const PdgParams &P)
+{
+    RandArgs a;
+    a.p = P.p; a.W = P.W; a.M = P.M; a.N = P.N; a.edges = P.edges; a.csr_off = P.csr_off; a.csr_adj = P.csr_adj;
+    a.err = P.err; a.chain0 = P.chain0; a.seed_lo = P.seed_lo; a.seed_hi = P.seed_hi;
+    return a;
+}
+
 // randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
 // shared memory.  Works on the global-memory state and rebuilds N and the CSR at the end.
-__device__ __forceinline__ void randomize_chain(const PdgParams &P, const RandScratch &Z, long long chain, u32 iter,
+__device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long long chain, u32 iter,
                                              unsigned char *smem, int lane)
 {
     const int p = P.p, W = P.W;
@@ -331,5 +351,5 @@ __device__ __forceinline__ void randomize_chain(const PdgParams &P, const RandSc
 __global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u32 iter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    randomize_chain(P, Z, blockIdx.x, iter, smem, threadIdx.x);
+    randomize_chain(rand_args(P), Z, blockIdx.x, iter, smem, threadIdx.x);
 }

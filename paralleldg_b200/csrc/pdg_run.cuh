@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             __syncwarp();
             if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
             __syncwarp();
-            randomize_chain(P, Z, chain, (u32)it, smem, lane);
+            randomize_chain(rand_args(P), Z, chain, (u32)it, smem, lane);
             __syncwarp();
             for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
             for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
