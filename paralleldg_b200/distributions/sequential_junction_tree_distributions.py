@@ -208,6 +208,10 @@ class GGMJTPosterior(_GPUScored):
         (wishart.py:24-30, ggm:36-39), k = 0..p."""
         from scipy.special import multigammaln
         delta, n, p = float(self.parameters["delta"]), float(self.n), self.p
+        key = (delta, n, p)
+        cached = getattr(self, "_gconst", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         out = np.zeros(p + 1, np.float64)
         for k in range(1, p + 1):
             t1 = (delta + n + k - 1.0) / 2.0
@@ -215,6 +219,7 @@ class GGMJTPosterior(_GPUScored):
             c1 = -t1 * k * np.log(np.pi) + multigammaln(t1, k)
             c2 = -t2 * k * np.log(np.pi) + multigammaln(t2, k)
             out[k] = c1 - c2
+        self._gconst = (key, out)
         return out
 
     def __str__(self):
