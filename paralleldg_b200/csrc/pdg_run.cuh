@@ -31,7 +31,7 @@
 
 struct RunSmem {
     int off_tri, off_idx, off_sub, off_leaf, off_bnd, off_partner, off_mvU, off_mvUadj, off_csr_off, off_csr_adj,
-        off_M, off_N, off_T, off_lidx, total;
+        off_M, off_N, off_T, off_lidx, off_tmpU, off_tmpA, off_cnt, total;
 };
 
 __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state)
@@ -59,6 +59,9 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state
     s.off_mvUadj = o;   o += a2;
     s.off_csr_off = o;  o += a2;
     s.off_csr_adj = o;  o += 2 * a2;
+    s.off_tmpU = o;     o += smem_state ? 0 : a2;      // unsorted boundary of the neighbourhood-driven scan
+    s.off_tmpA = o;     o += smem_state ? 0 : a2;
+    s.off_cnt = o;      o += 16;
     s.total = (o + 15) / 16 * 16;
     return s;
 }
@@ -159,6 +162,8 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     short *s_mvUadj = (short *)(smem + L.off_mvUadj);
     unsigned short *s_off = (unsigned short *)(smem + L.off_csr_off);
     unsigned short *s_adj = (unsigned short *)(smem + L.off_csr_adj);
+    short *s_tmpU = (short *)(smem + L.off_tmpU), *s_tmpA = (short *)(smem + L.off_tmpA);
+    int *s_cnt = (int *)(smem + L.off_cnt);
     WarpScratch ws;
     ws.tri32 = (double *)(smem + L.off_tri);
     ws.idx = (short *)(smem + L.off_idx);
@@ -246,6 +251,60 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
         // ---- one pass over the tree: leaves of the induced subtree / its outer boundary ------
         // (parallel_moves.py:193-208 and :253-272); proposals come out in ascending tree-node order
         int nm = 0, nleaf = 0, nbnd = 0;
+        if (!SMEM_STATE) {
+            // Large p (state in global memory): neighbourhood-driven enumeration.  List the few tree
+            // nodes of the subtree, walk only THEIR adjacency lists (leaves: exactly one neighbour
+            // inside; boundary: the neighbours outside), then rank-sort the boundary by tree node.
+            // O(|subtree| * degree) instead of a pass over all p tree nodes.
+            short *s_list = ws.idx;
+            for (int i = lane; i < nw32; i += 32) { s_leaf[i] = 0u; s_bnd[i] = 0u; }
+            if (lane == 0) *s_cnt = 0;
+            {
+                const int mine = (lane < W) ? __popcll(s_sub[lane]) : 0;
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(PDG_FULL, incl, o); if (lane >= o) incl += v; }
+                int off = incl - mine;
+                if (lane < W) {
+                    u64 x = s_sub[lane];
+                    while (x) { s_list[off++] = (short)(lane * 64 + __ffsll((long long)x) - 1); x &= x - 1; }
+                }
+            }
+            __syncwarp();
+            for (int i0 = 0; i0 < msub; i0 += 32) {
+                const int i = i0 + lane;
+                bool leaf = false;
+                int s = -1, last = -1;
+                if (i < msub) {
+                    s = s_list[i];
+                    int cnt = 0;
+                    for (int e = s_off[s]; e < s_off[s + 1]; ++e) {
+                        const int a = s_adj[e];
+                        if (bit32(s_sub32, a)) { ++cnt; last = a; }
+                        else { const int pos = atomicAdd(s_cnt, 1); s_tmpU[pos] = (short)a; s_tmpA[pos] = (short)s; }
+                    }
+                    leaf = cnt == 1;
+                    if (leaf) { s_partner[s] = (short)last; atomicOr(&s_leaf[s >> 5], 1u << (s & 31)); }
+                }
+                const u32 bl = __ballot_sync(PDG_FULL, leaf);
+                if (leaf && mtype == 1 && !special) {
+                    const int pos = nleaf + __popc(bl & lt);
+                    s_mvU[pos] = (short)s; s_mvUadj[pos] = (short)last;
+                }
+                nleaf += __popc(bl);
+            }
+            __syncwarp();
+            nbnd = *s_cnt;
+            for (int j = lane; j < nbnd; j += 32) {
+                const int U = s_tmpU[j], A = s_tmpA[j];
+                int rank = 0;
+                for (int i = 0; i < nbnd; ++i) rank += (s_tmpU[i] < U) ? 1 : 0;
+                s_partner[U] = (short)A;
+                atomicOr(&s_bnd[U >> 5], 1u << (U & 31));
+                if (mtype == 0 && !special) { s_mvU[rank] = (short)U; s_mvUadj[rank] = (short)A; }
+            }
+            nm = (mtype == 0) ? nbnd : nleaf;
+        } else
         for (int base = 0; base < p; base += 32) {
             const int t = base + lane;
             bool leaf = false, bnd = false;
@@ -253,20 +312,13 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             if (t < p) {
                 const int inT = bit32(s_sub32, t);
                 int cnt = 0;
-                if (SMEM_STATE) {
-                    // neighbours inside the subtree = adjacency row & subtree bitset
+                // neighbours inside the subtree = adjacency row & subtree bitset
 #pragma unroll
-                    for (int w = 0; w < WMAX; ++w) {
-                        if (w < W) {
-                            const u64 x = Tt[(size_t)t * W + w] & s_sub[w];
-                            cnt += __popcll(x);
-                            if (x && last < 0) last = w * 64 + __ffsll((long long)x) - 1;
-                        }
-                    }
-                } else {
-                    for (int e = s_off[t]; e < s_off[t + 1]; ++e) {
-                        const int a = s_adj[e];
-                        if (bit32(s_sub32, a)) { ++cnt; last = a; }
+                for (int w = 0; w < WMAX; ++w) {
+                    if (w < W) {
+                        const u64 x = Tt[(size_t)t * W + w] & s_sub[w];
+                        cnt += __popcll(x);
+                        if (x && last < 0) last = w * 64 + __ffsll((long long)x) - 1;
                     }
                 }
                 leaf = inT && cnt == 1;
