@@ -277,9 +277,10 @@ def main():
             h2d = int(inp["data"].size) + w["p"] * 4
         d2h = 0
         e_props = 0
-        for s in range(2):                                    # warm the pooled context
-            mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=seed + s, chain0=chain0, device=local_rank,
-                             rec_cap=cap, want_tallies=True, pooled=True)
+        batch = None
+        for s in range(max(args.warmup, 3)):                  # untimed warm-up of the same call: pooled
+            batch = mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=seed + s, chain0=chain0,   # context and
+                                     device=local_rank, rec_cap=cap, want_tallies=True, pooled=True)  # pinned buffers
         barrier()
         t0 = time.perf_counter()
         for s in range(args.steps):

@@ -26,7 +26,7 @@ __host__ __device__ inline InitSmem init_smem_layout(int p, int W)
     s.off_lidx = o; o += PDG_KT * 32 * 2;
 #else
     s.off_tri = o; o += 528 * 8;
-    s.off_lidx = o;
+    s.off_lidx = o; o += PDG_KT * 32 * 2;
 #endif
     s.off_sc = o; o += p * 8;
     s.off_ss = o; o += p * 8;
@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     ls.idx = (unsigned short *)(smem + PDG_KTRI * 32 * 8);
     ws.idx = (short *)(smem + PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2);
 #else
-    ls.a = nullptr; ls.idx = nullptr;
-    ws.idx = (short *)(smem + 528 * 8);
+    ls.a = nullptr;
+    ls.idx = (unsigned short *)(smem + 528 * 8);
+    ws.idx = (short *)(smem + 528 * 8 + PDG_KT * 32 * 2);
 #endif
     ws.kbig = P.kbig;
     const int slot = blockIdx.x;
@@ -370,7 +371,7 @@ static int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, dou
 #ifdef PDG_LANE_SMEM
     const int sm = PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
 #else
-    const int sm = 528 * 8 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+    const int sm = 528 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
 #endif
     k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
     ctx->launches++;

@@ -367,7 +367,8 @@ __device__ unsigned long long g_pt[8];
 #endif
 
 template <int K, int WMAX>
-__device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&X)[WMAX], int k, double &score)
+__device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const LaneScratch &ls, int lane, const u64 (&X)[WMAX], int k,
+                                                double &score)
 {
 #ifdef PDG_PHASE_TIMERS
     long long l0 = clock64(); unsigned long long lp[5] = {0, 0, 0, 0, 0};
@@ -378,18 +379,17 @@ __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const u64 (&
 #pragma unroll
         for (int t = 0; t < K; ++t) { idx[t] = y ? __ffsll((long long)y) - 1 : 0; y &= y - 1; }
     } else {
-        // multi-word keys: walk the words once with a dynamic counter into a small lane-private
-        // stack array (local memory, L1 resident), then read it back with static indices
-        int stk[K];
+        // multi-word keys: walk the words once with a dynamic counter into a lane-private column of
+        // shared memory (ls.idx[t * 32 + lane]), then read it back with static indices
+        unsigned short *stk = ls.idx + lane;
         int t = 0;
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) {
             u64 y = X[w];
-            while (y && t < K) { stk[t++] = w * 64 + __ffsll((long long)y) - 1; y &= y - 1; }
+            while (y && t < K) { stk[t * 32] = (unsigned short)(w * 64 + __ffsll((long long)y) - 1); ++t; y &= y - 1; }
         }
-        for (; t < K; ++t) stk[t] = 0;
 #pragma unroll
-        for (int q = 0; q < K; ++q) idx[q] = stk[q];
+        for (int q = 0; q < K; ++q) idx[q] = (q < t) ? (int)stk[q * 32] : 0;
     }
     LPT(0)
     double ld[2] = {0.0, 0.0};
@@ -460,9 +460,9 @@ __device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const LaneScr
 #endif
     const int kmax = (int)__reduce_max_sync(PDG_FULL, (unsigned)k);
     if (kmax == 0) { score = 0.0; return 0; }
-    if (kmax <= 4) return ggm_lane_score_k<4, WMAX>(P, X, k, score);
-    if (kmax <= 8) return ggm_lane_score_k<8, WMAX>(P, X, k, score);
-    return ggm_lane_score_k<12, WMAX>(P, X, k, score);
+    if (kmax <= 4) return ggm_lane_score_k<4, WMAX>(P, ls, lane, X, k, score);
+    if (kmax <= 8) return ggm_lane_score_k<8, WMAX>(P, ls, lane, X, k, score);
+    return ggm_lane_score_k<12, WMAX>(P, ls, lane, X, k, score);
 }
 
 template <int WMAX>

@@ -45,7 +45,7 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state
     s.off_lidx = o;     o += PDG_KT * 32 * 2;
 #else
     s.off_tri = o;      o += 528 * 8;
-    s.off_lidx = o;
+    s.off_lidx = o;     o += PDG_KT * 32 * 2;            // lane-private index columns (multi-word keys)
 #endif
     s.off_sub = o;      o += W * 8;
     s.off_M = o;        o += smem_state ? p * W * 8 : 0;
