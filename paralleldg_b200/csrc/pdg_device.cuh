@@ -17,7 +17,9 @@ enum { TAG_ITER = 0, TAG_MOVE = 1, TAG_PRUF_V = 2, TAG_PRUF_W = 3, TAG_PERM = 4,
 
 __device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 out[4])
 {
-#pragma unroll
+    // rounds deliberately NOT unrolled: the MH kernel is instruction-fetch bound and calls this from
+    // several places; the dynamic instruction count is the same
+#pragma unroll 1
     for (int r = 0; r < 10; ++r) {
         const u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
