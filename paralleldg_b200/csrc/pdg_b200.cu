@@ -793,10 +793,15 @@ int pdg_sample(pdg_ctx *ctx, int kind, int64_t randomize)
     if (M < 2) return PDG_OK;
     PdgReplayDev R;
     memset(&R, 0, sizeof(R));
-    if (!getenv("PDG_FUSED")) {
-        // default: one MH launch per randomisation interval with the randomiser as its own
-        // kernel in between (measured faster than the fused form below on B200: 174 vs 144 M
-        // proposals/s on the p = 50 GGM workload)
+    // One launch per randomisation interval (with the randomiser as its own kernel in between) or
+    // the whole run fused into ONE launch?  Separate launches re-align the chains every `randomize`
+    // iterations, which is what the instruction-fetch-bound GGM / small-table workloads want
+    // (p=50 GGM: 286 vs 279 M proposals/s, p=15 log-linear: 1196 vs 632 M/s); but every launch also
+    // waits for its slowest chain, and when a memo miss costs ~100 iterations (table scans over
+    // many rows) that tail dominates: p=100, n=1e5 log-linear runs 2.4x faster fused.
+    bool fused = ctx->P.model == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192;
+    if (const char *v = getenv("PDG_FUSED")) fused = atoi(v) != 0;
+    if (!fused) {
         long long it = 1;
         while (it < M) {
             if (it % randomize == 0 && (rc = pdg_randomize(ctx, (uint32_t)it))) return rc;
@@ -807,8 +812,8 @@ int pdg_sample(pdg_ctx *ctx, int kind, int64_t randomize)
         }
         return PDG_OK;
     }
-    // PDG_FUSED=1: the whole run in ONE launch, every warp carries its chain through all
-    // iterations and randomises its own junction tree every `randomize` iterations
+    // fused: every warp carries its chain through all iterations and randomises its own junction
+    // tree every `randomize` iterations
     return run_dispatch(ctx, kind, 1, M, R, randomize);
 }
 

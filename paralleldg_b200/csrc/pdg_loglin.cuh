@@ -21,7 +21,7 @@ template <int WMAX> struct KeyW { u64 w[WMAX]; };
 struct ScoreRes { double score; int err; };
 
 template <int WMAX>
-__device__ __noinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane)
+__device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane)
 {
     ScoreRes res; res.score = 0.0; res.err = 0;
     double score = 0.0;

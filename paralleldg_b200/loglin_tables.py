@@ -35,6 +35,19 @@ def distinct_cell_counts(levels, max_tables=MAX_TABLES):
 
 
 def build(sd):
+    """tables of one model; cached on the object (they depend only on data shape, levels and
+    cell_alpha) so that repeated sampler calls on the same model do not redo ~n lgamma calls per
+    table"""
+    key = (id(sd.data), float(sd.cell_alpha), tuple(int(l) for l in sd.no_levels))
+    cached = getattr(sd, "_gpu_tables", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    out = _build(sd)
+    sd._gpu_tables = (key, out)
+    return out
+
+
+def _build(sd):
     data = np.asarray(sd.data)
     n, p = data.shape
     levels = np.ascontiguousarray(np.asarray(sd.no_levels, dtype=np.int32))
