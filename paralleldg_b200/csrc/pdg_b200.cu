@@ -608,9 +608,13 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
         return e;
     };
     void *d_data = nullptr, *d_lv = nullptr, *d_k = nullptr, *d_a = nullptr, *d_lg = nullptr;
-    CK(own((size_t)P.p * nrows, &d_data));
+    // columns padded to a 16-byte stride, an all-zero column behind the last one and 4 KB of slack:
+    // the dense scan (pdg_loglin.cuh) then needs no load predicates
+    const size_t ld = ((size_t)nrows + 15) & ~(size_t)15;
+    CK(own((size_t)(P.p + 1) * ld + 4096, &d_data));
     CK(own((size_t)P.p * sizeof(int), &d_lv));
-    CK(cudaMemcpyAsync(d_data, data, (size_t)P.p * nrows, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemsetAsync(d_data, 0, (size_t)(P.p + 1) * ld + 4096, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_data, ld, data, (size_t)nrows, (size_t)nrows, (size_t)P.p, cudaMemcpyDefault, ctx->stream));
     CK(cudaMemcpyAsync(d_lv, levels, (size_t)P.p * sizeof(int), cudaMemcpyDefault, ctx->stream));
     if (n_ktab > 0) {
         CK(own((size_t)n_ktab * 8, &d_k));
@@ -623,7 +627,7 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     // dense cell counters: one table per warp slot (= chain); larger sets go through a pool of
     // hashed tables
     int hist_cells = 1 << 16;
-    if (const char *v = getenv("PDG_HIST_CELLS")) { const int x = atoi(v); if (x >= 2) hist_cells = x; }
+    if (const char *v = getenv("PDG_HIST_CELLS")) { const int x = atoi(v); if (x >= 2 && x <= (1 << 16)) hist_cells = x; }
     void *d_hist = nullptr;
     CK(own((size_t)P.n_chains * hist_cells * 4, &d_hist));
     CK(cudaMemsetAsync(d_hist, 0, (size_t)P.n_chains * hist_cells * 4, ctx->stream));
@@ -643,7 +647,7 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     CK(cudaMemsetAsync(d_cc, 0, (size_t)sp.nsp * (size_t)(nrows + 2) * 4, ctx->stream));
     sp.lock = (int *)d_lock; sp.hkeys = (u64 *)d_hk; sp.hcnt = (unsigned int *)d_hc; sp.cc = (unsigned int *)d_cc;
     CK(cudaStreamSynchronize(ctx->stream));
-    P.data = (const unsigned char *)d_data; P.levels = (const int *)d_lv; P.nrows = nrows; P.cell_alpha = cell_alpha;
+    P.data = (const unsigned char *)d_data; P.data_ld = (long long)ld; P.levels = (const int *)d_lv; P.nrows = nrows; P.cell_alpha = cell_alpha;
     P.n_ktab = n_ktab; P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
     P.hist = (unsigned int *)d_hist; P.hist_cells = hist_cells; P.sp = sp;
     P.model = PDG_MODEL_LOGLIN;

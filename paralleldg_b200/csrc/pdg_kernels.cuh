@@ -58,6 +58,7 @@ struct PdgParams {
     const unsigned char *data;  // [p][nrows] level codes, column-major
     const int *levels;          // [p]
     long long nrows;
+    long long data_ld;        // column stride of `data` (nrows rounded up to 16), zero column at index p
     double cell_alpha;
     int n_ktab;                 // lgamma tables: ktab[j] = cells, alphatab[j], lgtab[j][c]
     const double *ktab, *alphatab, *lgtab;

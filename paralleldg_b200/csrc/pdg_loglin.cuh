@@ -2,9 +2,9 @@
 // Restates discrete_dec_log_linear.py:12-70 + dirichlet.py:63-85 + auxiliary_functions.py:134-151:
 //   score(X) = sum over occupied cells [lgamma(n_cell + a) - lgamma(a)] - [lgamma(K a + N) - lgamma(K a)]
 // with K = prod of levels over X and a = cell_alpha * prod(levels outside X) / prod(all levels).
-// The scan reads the k level-code columns of X (column-major uint8, coalesced, 4 rows per lane
+// The scan reads the k level-code columns of X (column-major uint8, coalesced, 16 rows per lane
 // and load) once and counts cells with warp-wide atomics: into a dense per-warp table when
-// K <= hist_cells, else into a hashed table from a small lock-protected pool.  The lgamma terms
+// K <= hist_cells (<= 65536), else into a hashed table from a small lock-protected pool.  The lgamma terms
 // come from host-built tables (bit-identical to the reference's math.lgamma) when available.
 #pragma once
 #include "pdg_kernels.cuh"
@@ -13,12 +13,91 @@
 // register allocation -- the unrolled loads would otherwise spill the MH kernel -- and no address
 // of the kernel parameter block is taken).
 struct LoglinArgs {
-    const unsigned char *data; const int *levels; long long nrows; double cell_alpha;
+    const unsigned char *data; const int *levels; long long nrows, ld; int zero_col; double cell_alpha;
     int n_ktab; const double *ktab, *alphatab, *lgtab;
     unsigned int *hist; int hist_cells; LoglinSparse sp; unsigned long long *work; int W;
 };
 template <int WMAX> struct KeyW { u64 w[WMAX]; };
 struct ScoreRes { double score; int err; };
+
+// Dense counting pass.  The table is column-major uint8 with a 16-byte-aligned column stride `ld`,
+// zero padding below row n, one all-zero column behind the last real one and 4 KB of slack, so the
+// pass needs no column or load predicates: every lane reads 16 rows per load (uint4), a warp pass
+// covers 2048 rows of four columns (16 loads in flight per lane), missing columns of the last
+// chunk point at the zero column with multiplier 1.  Cell codes are built with PACKED arithmetic:
+// four rows per 32-bit multiply-add while codes fit a byte (K <= 256), two per multiply-add above.
+// The loads of the next chunk are issued before the current pass is counted.
+// Counting: shared-memory atomics into R interleaved replicas of the table (R * K <= 1024; lanes
+// l and l + R share one, so same-cell collisions inside a warp mostly disappear), or this warp's
+// table in global memory above 1024 cells.
+template <bool WIDE, bool GLB>
+__device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long long ld, long long n, int k,
+                                                   const unsigned int *colinfo, unsigned int *tab, int rshift, int lane)
+{
+    constexpr int NC = WIDE ? 2 : 1;
+    uint4 x[4][4];
+    auto issue = [&](long long base, int j0) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const unsigned char *col = D + (size_t)colinfo[16 + j0 + jj] * (size_t)ld + base + lane * 16;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[jj][u] = __ldg((const uint4 *)(col + 512 * u));
+        }
+    };
+    auto count1 = [&](unsigned int code) {
+        if (GLB) atomicAdd(&tab[code], 1u); else atomicAdd(&tab[code << rshift], 1u);
+    };
+    issue(0, 0);
+    for (long long base = 0; base < n; base += 2048) {
+        unsigned int c[4][4][NC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int h = 0; h < NC; ++h) c[u][q][h] = 0u;
+        for (int j0 = 0; j0 < k; j0 += 4) {
+            unsigned int L4[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) L4[jj] = colinfo[j0 + jj];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned int w[4] = {x[jj][u].x, x[jj][u].y, x[jj][u].z, x[jj][u].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (WIDE) {
+                            c[u][q][0] = c[u][q][0] * L4[jj] + __byte_perm(w[q], 0u, 0x4240);   // rows 4q, 4q+2
+                            c[u][q][NC - 1] = c[u][q][NC - 1] * L4[jj] + __byte_perm(w[q], 0u, 0x4341);   // rows 4q+1, 4q+3
+                        } else {
+                            c[u][q][0] = c[u][q][0] * L4[jj] + w[q];
+                        }
+                    }
+                }
+            }
+            const int nj0 = (j0 + 4 < k) ? j0 + 4 : 0;
+            const long long nbase = nj0 ? base : base + 2048;
+            if (nbase < n) issue(nbase, nj0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long r = base + 512 * u + lane * 16;
+            if (r < ld) {      // ld is a multiple of 16: the padding rows land in cell 0 and are subtracted by the caller
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (WIDE) {
+                        count1(c[u][q][0] & 0xffffu); count1(c[u][q][NC - 1] & 0xffffu);
+                        count1(c[u][q][0] >> 16); count1(c[u][q][NC - 1] >> 16);
+                    } else {
+                        count1(c[u][q][0] & 0xffu); count1((c[u][q][0] >> 8) & 0xffu);
+                        count1((c[u][q][0] >> 16) & 0xffu); count1(c[u][q][0] >> 24);
+                    }
+                }
+            }
+        }
+    }
+}
 
 template <int WMAX>
 __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane)
@@ -45,87 +124,36 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     const unsigned char *D = P.data;
     double acc = 0.0;
     if (!big && Ki <= (u64)P.hist_cells && k <= 16) {
-        // column ids and level counts in registers; every row block issues ALL its column loads
-        // before the first use (static unroll, predicated), so a block costs one L2 round trip
-        // instead of k dependent ones
-        int gc[16];
-        unsigned int Lv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { gc[j] = (j < k) ? (int)ws.idx[j] : 0; Lv[j] = (j < k) ? (unsigned int)P.levels[gc[j]] : 1u; }
-        // where the cells are counted: lane-private columns (<= 32 cells, no atomics), shared
-        // atomics (<= 1024 cells), or this warp's table in global memory
-        // (same-address global atomics serialise in L2 at ~100 ns each: a 64-cell table would cost
-        // ~10 ms per scan, so small tables are counted in shared memory)
-        const int mode = (Ki <= 32ull) ? 0 : (Ki <= 1024ull) ? 1 : 2;
+        // shared layout (the 528-double triangle buffer): 1024 counters, then 16 level counts and
+        // 16 column ids (slots past k: multiplier 1, the zero column)
         unsigned int *sh = (unsigned int *)ws.tri32;
-        unsigned int *hist = P.hist + (size_t)slot * P.hist_cells;      // all zero on entry
-        if (mode == 0) for (int c = lane; c < 32 * (int)Ki; c += 32) sh[c] = 0u;
-        if (mode == 1) for (int c = lane; c < (int)Ki; c += 32) sh[c] = 0u;
-        __syncwarp();
-        const bool vec = (n & 3) == 0;
-        auto count = [&](unsigned int c) {
-            if (mode == 0) sh[c * 32 + lane] += 1u;
-            else if (mode == 1) atomicAdd(&sh[c], 1u);
-            else atomicAdd(&hist[c], 1u);
-        };
-        if (vec) {
-            // 4 rows per lane and load (uchar4), EIGHT 128-row blocks in flight; the columns are taken
-            // four at a time in a warp-uniform loop, so one L2 round trip covers 32 loads and only
-            // ceil(k/4)*4 columns are ever touched.  Cell codes accumulate in registers.
-            for (long long r0 = (long long)lane * 4; r0 < n; r0 += 1024) {
-                unsigned int c[8][4];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { c[u][0] = 0u; c[u][1] = 0u; c[u][2] = 0u; c[u][3] = 0u; }
-                for (int j0 = 0; j0 < k; j0 += 4) {
-                    uchar4 x[8][4];
-                    unsigned int L4[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j0 + jj;
-                        const int g = (j < k) ? (int)ws.idx[j] : (int)ws.idx[0];
-                        L4[jj] = (j < k) ? (unsigned int)P.levels[g] : 1u;
-                        const unsigned char *col = D + (size_t)g * n + r0;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            x[u][jj] = make_uchar4(0, 0, 0, 0);
-                            if (j < k && r0 + 128 * u < n) x[u][jj] = __ldg((const uchar4 *)(col + 128 * u));
-                        }
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            c[u][0] = c[u][0] * L4[jj] + x[u][jj].x; c[u][1] = c[u][1] * L4[jj] + x[u][jj].y;
-                            c[u][2] = c[u][2] * L4[jj] + x[u][jj].z; c[u][3] = c[u][3] * L4[jj] + x[u][jj].w;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (r0 + 128 * u < n) { count(c[u][0]); count(c[u][1]); count(c[u][2]); count(c[u][3]); }
-                }
-            }
-        } else {
-            for (long long r = lane; r < n; r += 32) {
-                unsigned char x[16];
-                unsigned int c0 = 0u;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (j < k) x[j] = __ldg(D + (size_t)gc[j] * n + r);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (j < k) c0 = c0 * Lv[j] + x[j];
-                count(c0);
-            }
+        unsigned int *colinfo = sh + 1024;
+        if (lane < 16) {
+            const int g = (lane < k) ? (int)ws.idx[lane] : P.zero_col;
+            colinfo[lane] = (lane < k) ? (unsigned int)P.levels[g] : 1u;
+            colinfo[16 + lane] = (unsigned int)g;
         }
-        if (mode == 2) __threadfence();
+        const bool glb = Ki > 1024ull;
+        int rshift = 0;
+        if (!glb) while (rshift < 5 && (Ki << (rshift + 1)) <= 1024ull) ++rshift;
+        const int R = 1 << rshift;
+        unsigned int *hist = P.hist + (size_t)slot * P.hist_cells;      // all zero on entry
+        if (!glb) for (int c = lane; c < ((int)Ki << rshift); c += 32) sh[c] = 0u;
+        __syncwarp();
+        unsigned int *tab = glb ? hist : sh + (lane & (R - 1));
+        if (glb) loglin_count_dense<true, true>(D, P.ld, n, k, colinfo, tab, 0, lane);
+        else if (Ki > 256ull) loglin_count_dense<true, false>(D, P.ld, n, k, colinfo, tab, rshift, lane);
+        else loglin_count_dense<false, false>(D, P.ld, n, k, colinfo, tab, rshift, lane);
+        if (glb) __threadfence();
         __syncwarp();
         for (u64 c = lane; c < Ki; c += 32) {
             unsigned int cnt;
-            if (mode == 0) { cnt = 0u; for (int q = 0; q < 32; ++q) cnt += sh[(int)c * 32 + q]; }
-            else if (mode == 1) cnt = sh[c];
+            if (!glb) { cnt = 0u; for (int q = 0; q < R; ++q) cnt += sh[((int)c << rshift) + ((q + lane) & (R - 1))]; }
             else { cnt = __ldcg(&hist[c]); if (cnt) hist[c] = 0u; }
+            if (c == 0ull) cnt -= (unsigned int)(P.ld - n);      // zero padding rows of the last block
             if (cnt) acc += LG ? LG[cnt] : (lgamma((double)cnt + alpha) - lga);
         }
-        if (mode == 2) __threadfence();
+        if (glb) __threadfence();
         __syncwarp();
         score = warp_sum(acc) - constK;
         res.score = score;
@@ -147,7 +175,7 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     const u32 hmask = (u32)S.hslots - 1u;
     for (long long r = lane; r < n; r += 32) {
         u64 c = 0ull;
-        for (int j = 0; j < k; ++j) { const int g = ws.idx[j]; c = c * (u64)P.levels[g] + D[(size_t)g * n + r]; }
+        for (int j = 0; j < k; ++j) { const int g = ws.idx[j]; c = c * (u64)P.levels[g] + D[(size_t)g * (size_t)P.ld + r]; }
         const u64 key = c + 1ull;
         u32 h = (u32)mix64(key) & hmask;
         for (;;) {
@@ -192,7 +220,7 @@ __device__ __forceinline__ int loglin_set_score(const PdgParams &P, const WarpSc
                                                 const u64 (&X)[WMAX], int lane, double &score)
 {
     LoglinArgs A;
-    A.data = P.data; A.levels = P.levels; A.nrows = P.nrows; A.cell_alpha = P.cell_alpha;
+    A.data = P.data; A.levels = P.levels; A.nrows = P.nrows; A.ld = P.data_ld; A.zero_col = P.p; A.cell_alpha = P.cell_alpha;
     A.n_ktab = P.n_ktab; A.ktab = P.ktab; A.alphatab = P.alphatab; A.lgtab = P.lgtab;
     A.hist = P.hist; A.hist_cells = P.hist_cells; A.sp = P.sp; A.work = P.work; A.W = P.W;
     KeyW<WMAX> K;
