@@ -296,7 +296,7 @@ class Context(object):
         w = (C.c_int64 * 16)()
         self._ck(self.L.pdg_get_work(self.h, w))
         return dict(bytes=int(w[0]), flops=int(w[1]) / 6.0, sets=int(w[2]), sum_k=int(w[3]),
-                    sets_requested=int(w[4]), sum_k_requested=int(w[5]), sets_sparse=int(w[6]), phase=[int(x) for x in w[8:16]])
+                    sets_requested=int(w[4]), sum_k_requested=int(w[5]), sets_sparse=int(w[6]), sets_derived=int(w[7]), phase=[int(x) for x in w[8:16]])
 
     def launch_count(self):
         return int(self.L.pdg_launch_count(self.h))

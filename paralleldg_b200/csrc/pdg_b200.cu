@@ -17,7 +17,7 @@
 // nu_s * score(s) over the DISTINCT non-empty separators (first occurrence in edge order), plus
 // log_prior over cliques and distinct separators (seqdist:44-52).  One warp per chain.
 struct InitSmem { int off_tri, off_lidx, off_idx, off_sc, off_ss, off_cs, off_ssz, off_nu, off_first, total; };
-__host__ __device__ inline InitSmem init_smem_layout(int p, int W)
+__host__ __device__ inline InitSmem init_smem_layout(int p, int W, int tri_bytes)
 {
     InitSmem s; int o = 0;
     const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
@@ -25,7 +25,7 @@ __host__ __device__ inline InitSmem init_smem_layout(int p, int W)
     s.off_tri = o; o += PDG_KTRI * 32 * 8;
     s.off_lidx = o; o += PDG_KT * 32 * 2;
 #else
-    s.off_tri = o; o += 528 * 8;
+    s.off_tri = o; o += tri_bytes;
     s.off_lidx = o; o += PDG_KT * 32 * 2;
 #endif
     s.off_sc = o; o += p * 8;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
     extern __shared__ __align__(16) unsigned char smem[];
     const int p = P.p, W = P.W, lane = threadIdx.x;
     const long long chain = blockIdx.x;
-    const InitSmem L = init_smem_layout(p, W);
+    const InitSmem L = init_smem_layout(p, W, tri_bytes_for(P.ll_cap));
     double *s_sc = (double *)(smem + L.off_sc), *s_ss = (double *)(smem + L.off_ss);
     unsigned short *s_cs = (unsigned short *)(smem + L.off_cs), *s_ssz = (unsigned short *)(smem + L.off_ssz);
     unsigned short *s_nu = (unsigned short *)(smem + L.off_nu);
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     ws.idx = (short *)(smem + PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2);
 #else
     ls.a = nullptr;
-    ls.idx = (unsigned short *)(smem + 528 * 8);
-    ws.idx = (short *)(smem + 528 * 8 + PDG_KT * 32 * 2);
+    ls.idx = (unsigned short *)(smem + tri_bytes_for(P.ll_cap));
+    ws.idx = (short *)(smem + tri_bytes_for(P.ll_cap) + PDG_KT * 32 * 2);
 #endif
     ws.kbig = P.kbig;
     const int slot = blockIdx.x;
@@ -289,7 +289,7 @@ static int set_smem(pdg_ctx *ctx, F f, int bytes)
 template <int MODEL, int WMAX, bool SS>
 static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
-    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS);
+    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
     const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
     const int per_warp = (randomize > 0 && LR.total > L.total) ? LR.total : L.total;
     const int wpc = ctx->wpc, sm = per_warp * wpc;
@@ -344,7 +344,7 @@ static int run_dispatch(pdg_ctx *ctx, int kind, long long b, long long e, const 
 template <int MODEL, int WMAX>
 static int launch_init_t(pdg_ctx *ctx, int kind)
 {
-    const InitSmem L = init_smem_layout(ctx->P.p, ctx->P.W);
+    const InitSmem L = init_smem_layout(ctx->P.p, ctx->P.W, tri_bytes_for(ctx->P.ll_cap));
     int rc;
     if ((rc = set_smem(ctx, k_init_logl<MODEL, WMAX>, L.total))) return rc;
     k_init_logl<MODEL, WMAX><<<(unsigned)ctx->P.n_chains, 32, L.total, ctx->stream>>>(ctx->P, kind);
@@ -371,7 +371,7 @@ static int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, dou
 #ifdef PDG_LANE_SMEM
     const int sm = PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
 #else
-    const int sm = 528 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+    const int sm = tri_bytes_for(ctx->P.ll_cap) + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
 #endif
     k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
     ctx->launches++;
@@ -551,7 +551,7 @@ int pdg_set_prior(pdg_ctx *ctx, int prior_kind, double a, double b)
 int pdg_set_model_uniform(pdg_ctx *ctx)
 {
     if (!ctx) return PDG_E_ARG;
-    ctx->P.model = PDG_MODEL_UNIFORM;
+    ctx->P.model = PDG_MODEL_UNIFORM; ctx->P.ll_cap = 0;
     ctx->model_set = true;
     return PDG_OK;
 }
@@ -588,7 +588,7 @@ int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, dou
     CK(cudaStreamSynchronize(ctx->stream));
     P.A = ctx->d_A; P.Dm = ctx->d_D; P.logDdiag = ctx->d_logD; P.gconst = ctx->d_gconst;
     P.delta = delta; P.nobs = (double)n;
-    P.model = PDG_MODEL_GGM;
+    P.model = PDG_MODEL_GGM; P.ll_cap = 0;
     ctx->model_set = true;
     return PDG_OK;
 }
@@ -651,6 +651,16 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     P.n_ktab = n_ktab; P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
     P.hist = (unsigned int *)d_hist; P.hist_cells = hist_cells; P.sp = sp;
     P.model = PDG_MODEL_LOGLIN;
+    // per-warp shared count table: 4096 cells when a CTA of the MH kernel still fits in shared memory
+    P.ll_cap = 4096;
+    if (const char *v = getenv("PDG_LL_CAP")) { const int x = atoi(v); if (x >= 1024 && x <= 8192 && !(x & (x - 1))) P.ll_cap = x; }
+    for (;;) {
+        const RunSmem L = run_smem_layout(P.p, P.W, ctx->smem_state, tri_bytes_for(P.ll_cap));
+        const RandSmem LR = rand_smem_layout(P.p, P.W);
+        const int per_warp = LR.total > L.total ? LR.total : L.total;
+        if ((long long)per_warp * ctx->wpc <= 200 * 1024 || P.ll_cap <= 1024) break;
+        P.ll_cap >>= 1;
+    }
     ctx->model_set = true;
     return PDG_OK;
 }
@@ -1039,7 +1049,9 @@ int pdg_get_work(pdg_ctx *ctx, int64_t work[16])
     for (size_t c = 0; c < (size_t)ctx->P.n_chains; ++c) for (int q = 0; q < 16; ++q) work[q] += (int64_t)h[c * 16 + q];
 #ifdef PDG_PHASE_TIMERS
     { unsigned long long g[8]; cudaMemcpyFromSymbol(g, g_pt, sizeof(g));
-      fprintf(stderr, "lane scorer cycles: idx %llu gather %llu ldl %llu log %llu score %llu | calls K4 %llu K8 %llu\n", g[0], g[1], g[2], g[3], g[4], g[5], g[6]); }
+      fprintf(stderr, "lane scorer cycles: idx %llu gather %llu ldl %llu log %llu score %llu | calls K4 %llu K8 %llu\n", g[0], g[1], g[2], g[3], g[4], g[5], g[6]);
+      unsigned long long kh[2][32]; cudaMemcpyFromSymbol(kh, g_kh, sizeof(kh));
+      for (int k = 0; k < 32; ++k) if (kh[0][k]) fprintf(stderr, "  scans k=%d: %llu, %.0f cycles each\n", k, kh[0][k], (double)kh[1][k] / (double)kh[0][k]); }
 #endif
     return PDG_OK;
 }

@@ -59,6 +59,7 @@ struct PdgParams {
     const int *levels;          // [p]
     long long nrows;
     long long data_ld;        // column stride of `data` (nrows rounded up to 16), zero column at index p
+    int ll_cap;               // log-linear: cells of the per-warp shared count table (0 for other models)
     double cell_alpha;
     int n_ktab;                 // lgamma tables: ktab[j] = cells, alphatab[j], lgtab[j][c]
     const double *ktab, *alphatab, *lgtab;
@@ -222,9 +223,13 @@ __device__ __forceinline__ double ggm_score_from(const PdgParams &P, int k, doub
     return P.gconst[k] - t1 * ldA + t2 * ldD;
 }
 
+// bytes of the per-warp scratch region: the packed 32x32 triangle (GGM) or the log-linear count
+// table (`cap` counters + 48 words of column info, pdg_loglin.cuh)
+__host__ __device__ inline int tri_bytes_for(int ll_cap) { return ll_cap > 0 ? (ll_cap + 48) * 4 : 528 * 8; }
+
 // per-warp scratch: packed 32x32 triangle + index list
 struct WarpScratch {
-    double *tri32;            // 528 doubles (shared)
+    double *tri32;            // 528 doubles, or the log-linear count table (shared)
     short *idx;               // p + 1 entries (shared)
     double *big;              // global scratch for k > 32 (may be null)
     int kbig;

@@ -15,26 +15,45 @@
 struct LoglinArgs {
     const unsigned char *data; const int *levels; long long nrows, ld; int zero_col; double cell_alpha;
     int n_ktab; const double *ktab, *alphatab, *lgtab;
-    unsigned int *hist; int hist_cells; LoglinSparse sp; unsigned long long *work; int W;
+    unsigned int *hist; int hist_cells, cap; LoglinSparse sp; unsigned long long *work; int W;
 };
 template <int WMAX> struct KeyW { u64 w[WMAX]; };
+#ifdef PDG_PHASE_TIMERS
+__device__ unsigned long long g_kh[2][32];      // developer probe: scans and cycles by set size
+#endif
 struct ScoreRes { double score; int err; };
 
 // Dense counting pass.  The table is column-major uint8 with a 16-byte-aligned column stride `ld`,
 // zero padding below row n, one all-zero column behind the last real one and 4 KB of slack, so the
 // pass needs no column or load predicates: every lane reads 16 rows per load (uint4), a warp pass
-// covers 2048 rows of four columns (16 loads in flight per lane), missing columns of the last
-// chunk point at the zero column with multiplier 1.  Cell codes are built with PACKED arithmetic:
-// four rows per 32-bit multiply-add while codes fit a byte (K <= 256), two per multiply-add above.
+// covers 2048 rows of four column SLOTS (16 loads in flight per lane); empty slots point at the zero
+// column with multiplier 1.  Cell codes are built with PACKED arithmetic, four rows per 32-bit
+// multiply-add:
+//   MODE 0  K <= 256: one byte-packed accumulator per word;
+//   MODE 1  the columns split into two groups of <= 256 cells each (slots [0, slotsA) and the rest):
+//           two byte-packed accumulators, code = codeA * KB + codeB formed when counting;
+//   MODE 2  anything else up to 65536 cells: two 16-bit-packed accumulators per word.
 // The loads of the next chunk are issued before the current pass is counted.
-// Counting: shared-memory atomics into R interleaved replicas of the table (R * K <= 1024; lanes
+// Counting: shared-memory reductions into R interleaved replicas of the table (R * K <= cap; lanes
 // l and l + R share one, so same-cell collisions inside a warp mostly disappear), or this warp's
-// table in global memory above 1024 cells.
-template <bool WIDE, bool GLB>
-__device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long long ld, long long n, int k,
-                                                   const unsigned int *colinfo, unsigned int *tab, int rshift, int lane)
+// table in global memory above `cap` cells.
+struct LlCount {
+    int nslots, slotsA;         // column slots in use (multiple of 4), slots of the first group
+    unsigned int mulA, mulB;    // shared: byte strides of codeA / codeB; global: KB, 1
+    unsigned int sbase;         // shared-window byte address of this lane's replica (shared counting)
+    unsigned int *hist;         // this warp's table in global memory (global counting)
+};
+
+__device__ __forceinline__ void ll_red_shared(unsigned int addr)
 {
-    constexpr int NC = WIDE ? 2 : 1;
+    asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
+}
+
+template <int MODE, bool GLB>
+__device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long long ld, long long n, LlCount q,
+                                                   const unsigned int *colinfo, int lane)
+{
+    constexpr int NC = MODE == 0 ? 1 : 2;
     uint4 x[4][4];
     auto issue = [&](long long base, int j0) {
 #pragma unroll
@@ -44,8 +63,13 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
             for (int u = 0; u < 4; ++u) x[jj][u] = __ldg((const uint4 *)(col + 512 * u));
         }
     };
-    auto count1 = [&](unsigned int code) {
-        if (GLB) atomicAdd(&tab[code], 1u); else atomicAdd(&tab[code << rshift], 1u);
+    // a, b: this row's codeA / codeB (MODE 1) or the code and nothing (MODE 0, 2)
+    auto count1 = [&](unsigned int a, unsigned int b) {
+        if (GLB) {
+            if (MODE == 1) atomicAdd(&q.hist[a * q.mulA + b], 1u); else atomicAdd(&q.hist[a], 1u);
+        } else {
+            if (MODE == 1) ll_red_shared(a * q.mulA + (b * q.mulB + q.sbase)); else ll_red_shared(a * q.mulA + q.sbase);
+        }
     };
     issue(0, 0);
     for (long long base = 0; base < n; base += 2048) {
@@ -53,30 +77,34 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int w = 0; w < 4; ++w)
 #pragma unroll
-                for (int h = 0; h < NC; ++h) c[u][q][h] = 0u;
-        for (int j0 = 0; j0 < k; j0 += 4) {
+                for (int h = 0; h < NC; ++h) c[u][w][h] = 0u;
+        for (int j0 = 0; j0 < q.nslots; j0 += 4) {
             unsigned int L4[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) L4[jj] = colinfo[j0 + jj];
+            const bool grpA = j0 < q.slotsA;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const unsigned int w[4] = {x[jj][u].x, x[jj][u].y, x[jj][u].z, x[jj][u].w};
+                    const unsigned int w4[4] = {x[jj][u].x, x[jj][u].y, x[jj][u].z, x[jj][u].w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (WIDE) {
-                            c[u][q][0] = c[u][q][0] * L4[jj] + __byte_perm(w[q], 0u, 0x4240);   // rows 4q, 4q+2
-                            c[u][q][NC - 1] = c[u][q][NC - 1] * L4[jj] + __byte_perm(w[q], 0u, 0x4341);   // rows 4q+1, 4q+3
+                    for (int w = 0; w < 4; ++w) {
+                        if (MODE == 2) {
+                            c[u][w][0] = c[u][w][0] * L4[jj] + __byte_perm(w4[w], 0u, 0x4240);            // rows 4w, 4w+2
+                            c[u][w][NC - 1] = c[u][w][NC - 1] * L4[jj] + __byte_perm(w4[w], 0u, 0x4341);  // rows 4w+1, 4w+3
+                        } else if (MODE == 1) {
+                            if (grpA) c[u][w][0] = c[u][w][0] * L4[jj] + w4[w];
+                            else c[u][w][NC - 1] = c[u][w][NC - 1] * L4[jj] + w4[w];
                         } else {
-                            c[u][q][0] = c[u][q][0] * L4[jj] + w[q];
+                            c[u][w][0] = c[u][w][0] * L4[jj] + w4[w];
                         }
                     }
                 }
             }
-            const int nj0 = (j0 + 4 < k) ? j0 + 4 : 0;
+            const int nj0 = (j0 + 4 < q.nslots) ? j0 + 4 : 0;
             const long long nbase = nj0 ? base : base + 2048;
             if (nbase < n) issue(nbase, nj0);
         }
@@ -85,13 +113,13 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
             const long long r = base + 512 * u + lane * 16;
             if (r < ld) {      // ld is a multiple of 16: the padding rows land in cell 0 and are subtracted by the caller
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (WIDE) {
-                        count1(c[u][q][0] & 0xffffu); count1(c[u][q][NC - 1] & 0xffffu);
-                        count1(c[u][q][0] >> 16); count1(c[u][q][NC - 1] >> 16);
+                for (int w = 0; w < 4; ++w) {
+                    const unsigned int a = c[u][w][0], b = c[u][w][NC - 1];
+                    if (MODE == 2) {
+                        count1(a & 0xffffu, 0u); count1(b & 0xffffu, 0u); count1(a >> 16, 0u); count1(b >> 16, 0u);
                     } else {
-                        count1(c[u][q][0] & 0xffu); count1((c[u][q][0] >> 8) & 0xffu);
-                        count1((c[u][q][0] >> 16) & 0xffu); count1(c[u][q][0] >> 24);
+                        count1(a & 0xffu, b & 0xffu); count1((a >> 8) & 0xffu, (b >> 8) & 0xffu);
+                        count1((a >> 16) & 0xffu, (b >> 16) & 0xffu); count1(a >> 24, b >> 24);
                     }
                 }
             }
@@ -99,66 +127,188 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
     }
 }
 
+// sum over the cells of a count table of [lgamma(cnt + alpha) - lgamma(alpha)], minus the constant of
+// the set: the order (cells dealt to lanes, then a butterfly) is the same for scanned and derived tables
+struct LlConst { const double *LG; double alpha, constK, lga; };
+
+__device__ __forceinline__ LlConst ll_constants(const LoglinArgs &P, double Kd)
+{
+    LlConst r;
+    const long long n = P.nrows;
+    int tj = -1;
+    for (int j = 0; j < P.n_ktab; ++j) if (P.ktab[j] == Kd) tj = j;
+    r.LG = tj >= 0 ? P.lgtab + (size_t)tj * (size_t)(n + 2) : nullptr;
+    r.alpha = tj >= 0 ? P.alphatab[tj] : P.cell_alpha / Kd;
+    r.constK = tj >= 0 ? r.LG[n + 1] : lgamma(Kd * r.alpha + (double)n) - lgamma(Kd * r.alpha);
+    r.lga = r.LG ? 0.0 : lgamma(r.alpha);
+    return r;
+}
+
+__device__ __forceinline__ double ll_table_score(const LlConst &C, const unsigned int *tab, unsigned int cells, int lane)
+{
+    double acc = 0.0;
+    for (unsigned int c = lane; c < cells; c += 32) {
+        const unsigned int cnt = tab[c];
+        if (cnt) acc += C.LG ? C.LG[cnt] : (lgamma((double)cnt + C.alpha) - C.lga);
+    }
+    return warp_sum(acc) - C.constK;
+}
+
+// What the last dense scan left behind: when `cells` > 0 the exact count table of the set whose
+// sorted column list is still in ws.idx sits compact in shared memory at sh[0 .. cells).
+struct LlTable { unsigned int cells; int k; };
+
+// Score of a proper subset Z of the set whose table `t` describes, by summing the other columns out
+// of the table one at a time (ping-pong buffers behind the table; cells <= cap / 2).  The counts are
+// exact integers, so the score is bit-identical to what a scan of Z's own columns gives.
 template <int WMAX>
-__device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane)
+__device__ __forceinline__ double loglin_derive(const LoglinArgs &P, const WarpScratch &ws, const LlTable &t,
+                                                const KeyW<WMAX> &Z, int lane)
+{
+    unsigned int *sh = (unsigned int *)ws.tri32;
+    const unsigned int *colinfo = sh + P.cap + 32;         // levels of the table's columns by rank
+    const int k = t.k;
+    // which ranks stay
+    bool keep = false;
+    if (lane < k) {
+        const int g = ws.idx[lane];
+        u64 zw = 0ull;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) zw |= Z.w[w] & (0ull - (u64)((g >> 6) == w));     // (no dynamic register indexing)
+        keep = (zw >> (g & 63)) & 1ull;
+    }
+    const u32 zmask = __ballot_sync(PDG_FULL, keep);
+    const unsigned int *src = sh;
+    unsigned int *bufA = sh + t.cells, *bufB = sh + t.cells + (t.cells >> 1);
+    unsigned int *dst = bufA;
+    unsigned int hi = 1u;            // cells of the kept columns before rank j
+    unsigned int lo = t.cells;       // cells of the columns from rank j on (all still present)
+    double Kd = 1.0;
+    for (int j = 0; j < k; ++j) {
+        const unsigned int L = colinfo[j];
+        lo /= L;                     // now: cells of the columns after rank j
+        if ((zmask >> j) & 1u) { hi *= L; Kd *= (double)L; continue; }
+        if (L == 1u) continue;
+        const unsigned int nout = hi * lo;
+        for (unsigned int o = lane; o < nout; o += 32) {
+            const unsigned int h = o / lo, l = o - h * lo;
+            const unsigned int *in = src + (size_t)h * L * lo + l;
+            unsigned int sum = 0u;
+            for (unsigned int d = 0; d < L; ++d) sum += in[(size_t)d * lo];
+            dst[o] = sum;
+        }
+        __syncwarp();
+        src = dst;
+        dst = (dst == bufA) ? bufB : bufA;
+    }
+    const LlConst C = ll_constants(P, Kd);
+    const double sc = ll_table_score(C, src, hi, lane);
+    __syncwarp();
+    return sc;
+}
+
+template <int WMAX>
+__device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane, LlTable &tout)
 {
     ScoreRes res; res.score = 0.0; res.err = 0;
+    tout.cells = 0u; tout.k = 0;
     double score = 0.0;
+#ifdef PDG_PHASE_TIMERS
+    const long long kh_t0 = clock64();
+#endif
     const int k = build_index_sorted<WMAX>(XK.w, P.W, lane, ws.idx);
     if (k == 0) return res;
     const long long n = P.nrows;
     double Kd = 1.0;
     u64 Ki = 1ull;
     bool big = false;
+    // greedy split into two column groups of <= 256 cells each (byte-packed codes)
+    int nA = 0;
+    unsigned int prodA = 1u, prodB = 1u;
+    bool splitB = false, twoOk = true;
     for (int j = 0; j < k; ++j) {
         const u64 Lj = (u64)P.levels[ws.idx[j]];
         Kd *= (double)Lj;
         if (Ki > (1ull << 62) / Lj) big = true; else Ki *= Lj;
+        if (!splitB && (u64)prodA * Lj <= 256ull) { prodA *= (unsigned int)Lj; ++nA; }
+        else { splitB = true; if ((u64)prodB * Lj <= 256ull) prodB *= (unsigned int)Lj; else twoOk = false; }
     }
-    int tj = -1;
-    for (int j = 0; j < P.n_ktab; ++j) if (P.ktab[j] == Kd) tj = j;
-    const double *LG = tj >= 0 ? P.lgtab + (size_t)tj * (size_t)(n + 2) : nullptr;
-    const double alpha = tj >= 0 ? P.alphatab[tj] : P.cell_alpha / Kd;
-    const double constK = tj >= 0 ? LG[n + 1] : lgamma(Kd * alpha + (double)n) - lgamma(Kd * alpha);
-    const double lga = LG ? 0.0 : lgamma(alpha);
+    const LlConst C = ll_constants(P, Kd);
     const unsigned char *D = P.data;
     double acc = 0.0;
     if (!big && Ki <= (u64)P.hist_cells && k <= 16) {
-        // shared layout (the 528-double triangle buffer): 1024 counters, then 16 level counts and
-        // 16 column ids (slots past k: multiplier 1, the zero column)
+        // shared layout: `cap` counters, then 16 multipliers and 16 column ids by SLOT and the 16
+        // levels of the columns by RANK (for loglin_derive)
         unsigned int *sh = (unsigned int *)ws.tri32;
-        unsigned int *colinfo = sh + 1024;
+        unsigned int *colinfo = sh + P.cap;
+        const int slotsA = (nA + 3) & ~3, slotsB = (k - nA + 3) & ~3;
+        twoOk = twoOk && slotsA + slotsB <= 16;
+        const int mode = (Ki <= 256ull) ? 0 : twoOk ? 1 : 2;
         if (lane < 16) {
-            const int g = (lane < k) ? (int)ws.idx[lane] : P.zero_col;
-            colinfo[lane] = (lane < k) ? (unsigned int)P.levels[g] : 1u;
+            int j = lane;                                   // rank held by this slot, -1: empty
+            if (mode == 1) j = lane < slotsA ? (lane < nA ? lane : -1) : (nA + lane - slotsA < k ? nA + lane - slotsA : -1);
+            else if (lane >= k) j = -1;
+            const int g = j >= 0 ? (int)ws.idx[j] : P.zero_col;
+            colinfo[lane] = j >= 0 ? (unsigned int)P.levels[g] : 1u;
             colinfo[16 + lane] = (unsigned int)g;
+            colinfo[32 + lane] = lane < k ? (unsigned int)P.levels[ws.idx[lane]] : 1u;
         }
-        const bool glb = Ki > 1024ull;
+        const bool glb = Ki > (u64)P.cap;
         int rshift = 0;
-        if (!glb) while (rshift < 5 && (Ki << (rshift + 1)) <= 1024ull) ++rshift;
+        if (!glb) while (rshift < 5 && (Ki << (rshift + 1)) <= (u64)P.cap) ++rshift;
         const int R = 1 << rshift;
         unsigned int *hist = P.hist + (size_t)slot * P.hist_cells;      // all zero on entry
         if (!glb) for (int c = lane; c < ((int)Ki << rshift); c += 32) sh[c] = 0u;
         __syncwarp();
-        unsigned int *tab = glb ? hist : sh + (lane & (R - 1));
-        if (glb) loglin_count_dense<true, true>(D, P.ld, n, k, colinfo, tab, 0, lane);
-        else if (Ki > 256ull) loglin_count_dense<true, false>(D, P.ld, n, k, colinfo, tab, rshift, lane);
-        else loglin_count_dense<false, false>(D, P.ld, n, k, colinfo, tab, rshift, lane);
-        if (glb) __threadfence();
+        LlCount q;
+        q.nslots = mode == 1 ? slotsA + slotsB : (k + 3) & ~3;
+        q.slotsA = mode == 1 ? slotsA : q.nslots;
+        q.hist = hist;
+        q.sbase = (unsigned int)__cvta_generic_to_shared(sh) + 4u * (unsigned int)(lane & (R - 1));
+        if (glb) { q.mulA = mode == 1 ? prodB : 1u; q.mulB = 1u; }
+        else { q.mulB = 4u << rshift; q.mulA = mode == 1 ? prodB * q.mulB : q.mulB; }
+        if (mode == 0) loglin_count_dense<0, false>(D, P.ld, n, q, colinfo, lane);
+        else if (mode == 1 && !glb) loglin_count_dense<1, false>(D, P.ld, n, q, colinfo, lane);
+        else if (mode == 1) loglin_count_dense<1, true>(D, P.ld, n, q, colinfo, lane);
+        else if (!glb) loglin_count_dense<2, false>(D, P.ld, n, q, colinfo, lane);
+        else loglin_count_dense<2, true>(D, P.ld, n, q, colinfo, lane);
         __syncwarp();
-        for (u64 c = lane; c < Ki; c += 32) {
-            unsigned int cnt;
-            if (!glb) { cnt = 0u; for (int q = 0; q < R; ++q) cnt += sh[((int)c << rshift) + ((q + lane) & (R - 1))]; }
-            else { cnt = __ldcg(&hist[c]); if (cnt) hist[c] = 0u; }
-            if (c == 0ull) cnt -= (unsigned int)(P.ld - n);      // zero padding rows of the last block
-            if (cnt) acc += LG ? LG[cnt] : (lgamma((double)cnt + alpha) - lga);
+        if (!glb) {
+            // fold the replicas into a compact table sh[0 .. Ki) (32 cells at a time: all reads of a
+            // round come before its writes, and a round only overwrites replicas already folded)
+            const unsigned int pad = (unsigned int)(P.ld - n);      // zero padding rows of the last block
+            for (unsigned int c0 = 0; c0 < (unsigned int)Ki; c0 += 32) {
+                const unsigned int c = c0 + lane;
+                unsigned int cnt = 0u;
+                if (c < (unsigned int)Ki) for (int r = 0; r < R; ++r) cnt += sh[(c << rshift) + ((r + lane) & (R - 1))];
+                if (c == 0u) cnt -= pad;
+                __syncwarp();
+                if (c < (unsigned int)Ki) sh[c] = cnt;
+                __syncwarp();
+            }
+            score = ll_table_score(C, sh, (unsigned int)Ki, lane);
+            if (2ull * Ki <= (u64)P.cap) { tout.cells = (unsigned int)Ki; tout.k = k; }
+        } else {
+            __threadfence();
+            __syncwarp();
+            for (u64 c = lane; c < Ki; c += 32) {
+                unsigned int cnt = __ldcg(&hist[c]);
+                if (cnt) hist[c] = 0u;
+                if (c == 0ull) cnt -= (unsigned int)(P.ld - n);
+                if (cnt) acc += C.LG ? C.LG[cnt] : (lgamma((double)cnt + C.alpha) - C.lga);
+            }
+            __threadfence();
+            __syncwarp();
+            score = warp_sum(acc) - C.constK;
         }
-        if (glb) __threadfence();
-        __syncwarp();
-        score = warp_sum(acc) - constK;
         res.score = score;
+#ifdef PDG_PHASE_TIMERS
+        if (lane == 0) { atomicAdd(&g_kh[0][k < 31 ? k : 31], 1ull); atomicAdd(&g_kh[1][k < 31 ? k : 31], (unsigned long long)(clock64() - kh_t0)); }
+#endif
         return res;
     }
+    const double *LG = C.LG;
+    const double alpha = C.alpha, constK = C.constK, lga = C.lga;
     if (big) { res.err = ERR_BIGCLIQUE; return res; }            // cell codes beyond 62 bits
     if (lane == 0) atomicAdd(&P.work[(size_t)slot * 16 + 6], 1ull);       // sets that needed the hashed-cell pool
     // ---- sparse path: hashed cells, then a count-of-counts pass for an order-free sum ----------
@@ -214,19 +364,34 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
 }
 
 
-// inlined shim used by the kernels
-template <int WMAX>
-__device__ __forceinline__ int loglin_set_score(const PdgParams &P, const WarpScratch &ws, int slot,
-                                                const u64 (&X)[WMAX], int lane, double &score)
+// inlined shims used by the kernels
+__device__ __forceinline__ LoglinArgs loglin_args(const PdgParams &P)
 {
     LoglinArgs A;
     A.data = P.data; A.levels = P.levels; A.nrows = P.nrows; A.ld = P.data_ld; A.zero_col = P.p; A.cell_alpha = P.cell_alpha;
     A.n_ktab = P.n_ktab; A.ktab = P.ktab; A.alphatab = P.alphatab; A.lgtab = P.lgtab;
-    A.hist = P.hist; A.hist_cells = P.hist_cells; A.sp = P.sp; A.work = P.work; A.W = P.W;
+    A.hist = P.hist; A.hist_cells = P.hist_cells; A.cap = P.ll_cap; A.sp = P.sp; A.work = P.work; A.W = P.W;
+    return A;
+}
+
+template <int WMAX>
+__device__ __forceinline__ int loglin_set_score(const PdgParams &P, const WarpScratch &ws, int slot,
+                                                const u64 (&X)[WMAX], int lane, double &score, LlTable &t)
+{
     KeyW<WMAX> K;
 #pragma unroll
     for (int w = 0; w < WMAX; ++w) K.w[w] = X[w];
-    const ScoreRes r = loglin_scan<WMAX>(A, ws, slot, K, lane);
+    const ScoreRes r = loglin_scan<WMAX>(loglin_args(P), ws, slot, K, lane, t);
     score = r.score;
     return r.err;
+}
+
+template <int WMAX>
+__device__ __forceinline__ double loglin_subset_score(const PdgParams &P, const WarpScratch &ws, const LlTable &t,
+                                                      const u64 (&Z)[WMAX], int lane)
+{
+    KeyW<WMAX> K;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) K.w[w] = Z[w];
+    return loglin_derive<WMAX>(loglin_args(P), ws, t, K, lane);
 }

@@ -34,7 +34,7 @@ struct RunSmem {
         off_M, off_N, off_T, off_lidx, off_tmpU, off_tmpA, off_cnt, total;
 };
 
-__host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state)
+__host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state, int tri_bytes)
 {
     RunSmem s;
     int o = 0;
@@ -44,7 +44,7 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state
     s.off_tri = o;      o += PDG_KTRI * 32 * 8;          // lane-private triangles (alias the 32x32 warp triangle)
     s.off_lidx = o;     o += PDG_KT * 32 * 2;
 #else
-    s.off_tri = o;      o += 528 * 8;
+    s.off_tri = o;      o += tri_bytes;
     s.off_lidx = o;     o += PDG_KT * 32 * 2;            // lane-private index columns (multi-word keys)
 #endif
     s.off_sub = o;      o += W * 8;
@@ -109,14 +109,21 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     if (need) hit = memo_lookup<WMAX>(P.memo, X, W, score);
     u32 miss = __ballot_sync(PDG_FULL, need && !hit);
     while (miss) {
-        const int src = __ffs((int)miss) - 1;
+        int src = __ffs((int)miss) - 1;
+        if (MODEL == PDG_MODEL_LOGLIN) {
+            // largest missing set first: the smaller ones that are its subsets are then read off its
+            // count table instead of being scanned
+            const int kmax = __reduce_max_sync(PDG_FULL, (need && !hit) ? kq : 0);
+            src = __ffs((int)__ballot_sync(PDG_FULL, need && !hit && kq == kmax)) - 1;
+        }
         u64 Y[WMAX];
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) Y[w] = __shfl_sync(PDG_FULL, X[w], src);
         double sc = 0.0;
         int e;
+        LlTable tab; tab.cells = 0u; tab.k = 0;
         if (MODEL == PDG_MODEL_GGM) e = ggm_set_score<WMAX>(P, ws, Y, lane, sc);
-        else e = loglin_set_score<WMAX>(P, ws, slot, Y, lane, sc);
+        else e = loglin_set_score<WMAX>(P, ws, slot, Y, lane, sc, tab);
         err |= e;
         if (lane == 0) {
             if (!e) memo_insert<WMAX>(P.memo, Y, W, sc);
@@ -137,6 +144,25 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) same = same && (X[w] == Y[w]);
         if (same) { score = sc; hit = true; }
+        if (MODEL == PDG_MODEL_LOGLIN && tab.cells && !e) {
+            for (;;) {
+                bool sub = need && !hit;
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) sub = sub && ((X[w] & ~Y[w]) == 0ull);
+                const u32 subs = __ballot_sync(PDG_FULL, sub);
+                if (!subs) break;
+                const int zs = __ffs((int)subs) - 1;
+                u64 Zk[WMAX];
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) Zk[w] = __shfl_sync(PDG_FULL, X[w], zs);
+                const double sz = loglin_subset_score<WMAX>(P, ws, tab, Zk, lane);
+                if (lane == 0) { memo_insert<WMAX>(P.memo, Zk, W, sz); wk[7] += 1ull; }
+                bool sm = need && !hit;
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) sm = sm && (X[w] == Zk[w]);
+                if (sm) { score = sz; hit = true; }
+            }
+        }
         miss = __ballot_sync(PDG_FULL, need && !hit);
     }
     return err;
@@ -151,7 +177,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const long long chain = (long long)blockIdx.x * wpc + warp;
     if (chain >= P.n_chains) return;                       // (lockstep is only set when no warp exits here)
-    const RunSmem L = run_smem_layout(p, W, SMEM_STATE);
+    const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
     unsigned char *smem = smem_all + (size_t)warp * smem_per_warp;
     u64 *s_sub = (u64 *)(smem + L.off_sub);
     u32 *s_sub32 = (u32 *)(smem + L.off_sub);
@@ -511,7 +537,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     if (lane == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
     // work counters are kept per lane: reduce over the warp, one atomic per counter
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
+    for (int q = 0; q < 8; ++q) {
         unsigned long long v = wk[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PDG_FULL, v, o);
         if (lane == 0 && v) atomicAdd(&P.work[chain * 16 + q], v);

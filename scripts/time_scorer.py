@@ -18,7 +18,7 @@ ctx = nat.Context(p, 1024, 1, rec_cap=0)
 engine.configure_model(ctx, sd)
 W = ctx.W
 for k in [int(x) for x in (sys.argv[4].split(",") if len(sys.argv) > 4 else "2,4,6,8,12,16".split(","))]:
-    ns = 4096 if model == "loglin" else 1 << 18
+    ns = int(os.environ.get("TS_NS", "4096")) if model == "loglin" else 1 << 18
     import ctypes as C
     d_out = torch.empty(ns, dtype=torch.float64, device="cuda")
     for rep in range(3):
@@ -34,7 +34,7 @@ for k in [int(x) for x in (sys.argv[4].split(",") if len(sys.argv) > 4 else "2,4
         torch.cuda.synchronize(); dt = time.perf_counter() - t
     assert rc == 0
     if model == "loglin":
-        print("loglin p=%d n=%d k=%d: %d sets in %.2f ms -> %.1f us/set/warp-slot(1024 warps)  algorithmic %.1f GB/s" % (p, n, k, ns, dt * 1e3, dt * 1e6 / ns * 1024, ns * n * k / dt / 1e9))
+        print("loglin p=%d n=%d k=%d: %d sets in %.2f ms -> %.1f us per scan per warp (32 sets per warp, <= 1024 warps)  algorithmic %.1f GB/s" % (p, n, k, ns, dt * 1e3, dt * 1e6 / ns * min(1024, ns // 32), ns * n * k / dt / 1e9))
     else:
         fl = ns * (k ** 3 / 3.0 + k * k / 2.0 + k)
         print("ggm p=%d k=%d: %d sets in %.2f ms -> %.1f Msets/s  %.1f GFLOP/s fp64  algorithmic %.1f GB/s" % (p, k, ns, dt * 1e3, ns / dt / 1e6, fl / dt / 1e9, ns * 8 * k * k / dt / 1e9))
