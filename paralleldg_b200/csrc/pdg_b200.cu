@@ -301,7 +301,7 @@ static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const 
     int lockstep = 0;
     // (not for log-linear models with many rows: a table scan then costs ~100x an iteration and the
     // other chains of the CTA must not wait for it)
-    if (wpc > 1 && (long long)grid * wpc == ctx->P.n_chains && !(MODEL == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192)) {
+    if (wpc > 1 && !(MODEL == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192)) {
         lockstep = 16;
         if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
         if (lockstep & (lockstep - 1)) lockstep = 0;
@@ -433,7 +433,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     if (device < 0 || device >= ndev) return PDG_E_ARG;
     pdg_ctx *ctx = new pdg_ctx();
     ctx->device = device;
-    ctx->wpc = (n_chains % 8 == 0) ? 8 : (n_chains % 4 == 0) ? 4 : 1;
+    ctx->wpc = n_chains >= 8 ? 8 : (int)n_chains;      // the last CTA may be partial (its barrier counts live warps)
     if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) ctx->wpc = x; }
     // 16M slots (256 MB) for one- and two-word keys: the p = 50 hit rate saturates at 2^23; wider
     // keys come with far more distinct cliques (p = 500: 21M per run), 32M slots = 2.7 GB there

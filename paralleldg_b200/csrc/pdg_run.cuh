@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
     const int p = P.p, W = P.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const long long chain = (long long)blockIdx.x * wpc + warp;
-    if (chain >= P.n_chains) return;                       // (lockstep is only set when no warp exits here)
+    if (chain >= P.n_chains) return;                       // (the re-alignment barrier below counts live warps only)
+    const int live_threads = 32 * (int)(((long long)(blockIdx.x + 1) * wpc <= P.n_chains) ? wpc : (P.n_chains - (long long)blockIdx.x * wpc));
     const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
     unsigned char *smem = smem_all + (size_t)warp * smem_per_warp;
     u64 *s_sub = (u64 *)(smem + L.off_sub);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
         // chains of one CTA re-align every `lockstep` iterations: the loop body is larger than the
         // L1.5 instruction cache, loosely in step the warps share its fetches instead of each
         // streaming it (measured: fused single-launch runs go from 228 to 293 M proposals/s)
-        if (lockstep && ((it - it_begin) & (lockstep - 1)) == 0) __syncthreads();
+        if (lockstep && ((it - it_begin) & (lockstep - 1)) == 0) asm volatile("bar.sync 1, %0;" :: "r"(live_threads) : "memory");
         // ---- junction-tree randomisation every `randomize` iterations (mh_parallel.py:226-228),
         // fused here so that a whole run is ONE launch and no chain ever waits for another.  The
         // randomiser works on the global-memory state and reuses this warp's shared memory.
