@@ -44,6 +44,33 @@ def loglin_case(ref, name, data, n_levels, kind, M, R, seed, prior=("mbc", 2.0, 
     return log
 
 
+def loglin_batch(ref, name, data, n_levels, kind, M, R, seeds, prior=("mbc", 2.0, 4.0), pseudo_obs=1.0):
+    """Many independent reference chains on the same data in ONE fixture (config 3: every chain of a
+    batch replays its own reference log).  Ragged per-chain arrays are concatenated with offsets."""
+    levels = np.array([range(l) for l in n_levels])
+    logs = []
+    for seed in seeds:
+        sd = ref.seqdist.LogLinearJTPosterior()
+        sd.init_model(np.asarray(data), pseudo_obs, levels, {}, {})
+        sdg = ref.mh.get_prior(list(prior))
+        log, traj = rs.trace_chain(kind, M, R, sd, sdg, seed=seed)
+        logs.append(log)
+    fixed = ("state_edges", "state_bits", "it_node", "it_mtype_raw", "it_aux", "it_off", "logl")
+    ragged_mv = ("mv_U", "mv_Uadj", "mv_u", "mv_dlik", "mv_dprior", "mv_logq")
+    ragged_up = ("upd_i", "upd_k", "upd_type", "upd_node", "upd_C", "upd_Cadj")
+    out = {k: np.stack([l[k] for l in logs]) for k in fixed}
+    for k in ragged_mv + ragged_up:
+        out[k] = np.concatenate([l[k] for l in logs])
+    out["mv_off"] = np.concatenate([[0], np.cumsum([len(l["mv_U"]) for l in logs])]).astype(np.int64)
+    out["upd_off"] = np.concatenate([[0], np.cumsum([len(l["upd_i"]) for l in logs])]).astype(np.int64)
+    out["n_updates"] = np.array([int(l["n_updates"]) for l in logs], dtype=np.int64)
+    l0 = logs[0]
+    save(name, model=np.array("loglin"), data=np.asarray(data, dtype=np.uint8),
+         levels=np.asarray(n_levels, dtype=np.int32), cell_alpha=np.float64(pseudo_obs), prior=prior_arr(prior),
+         p=l0["p"], n_samples=l0["n_samples"], randomize=l0["randomize"], single=l0["single"],
+         state_iter=l0["state_iter"], seeds=np.asarray(list(seeds), dtype=np.int64), **out)
+
+
 def ggm_case(ref, name, X, kind, M, R, seed, prior=("mbc", 2.0, 4.0), delta=1.0, D=None, init_graph=None):
     X = np.asarray(X, dtype=np.float64)
     p = X.shape[1]
@@ -299,6 +326,10 @@ def main():
         for seed in (0, 1, 2, 3):
             loglin_case(ref, "cfg3_p15_parallel_s%d" % seed, df.to_numpy(), nl, "parallel", 2500, 100, seed)
         loglin_case(ref, "cfg3_p15_single_s5", df.to_numpy(), nl, "single", 2500, 100, 5)
+    if want("p15batch"):
+        df = pd.read_csv(os.path.join(REFDATA, "discrete_loglin_p15.csv"), sep=",", header=[0, 1])
+        nl = np.array(df.columns.get_level_values(1), dtype=int)
+        loglin_batch(ref, "batch_cfg3_p15_parallel_32chains", df.to_numpy(), nl, "parallel", 1000, 100, range(100, 132))
     if want("ggm50"):
         # config 2: the CLI reads the CSV with header=0, so n = 99 (bin/parallelDG_ggm_sample:21)
         df = pd.read_csv(os.path.join(REFDATA, "AR1-5_p_50_sigma2_1.0_rho_0.9_n_100.csv"))

@@ -77,3 +77,43 @@ def run_gpu_replay(g, n_chains=2):
                state=ctx.get_state(), launches=ctx.launch_count())
     ctx.close()
     return out
+
+
+def run_gpu_replay_batch(g, reps=1):
+    """Replays a batch fixture (every chain its own reference log) in ONE context; `reps` tiles the
+    batch so that more chains than logs run at once.  Returns the same dict as run_gpu_replay."""
+    from tests.helpers import batch_chain_log
+    C0 = len(g["n_updates"])
+    logs = [batch_chain_log(g, c) for c in range(C0)] * reps
+    C = len(logs)
+    sd, sdg = product_sd(g), product_prior(g)
+    M, R = int(g["n_samples"]), int(g["randomize"])
+    kind = KIND[int(g["single"])]
+    ctx = engine.make_context(sd, sdg, C, M, seed=0, rec_cap=max(len(l["upd_i"]) for l in logs) + 8)
+    ctx.enable_move_log(max(int(l["n_updates"]) for l in logs) + 2)
+    rp = dict(n_samples=M)
+    rp["it_node"] = np.stack([l["it_node"] for l in logs])
+    rp["it_mtype"] = np.stack([l["it_mtype_raw"] for l in logs])
+    rp["it_aux"] = np.stack([l["it_aux"] for l in logs])
+    mv_off = np.concatenate([[0], np.cumsum([len(l["mv_U"]) for l in logs])])
+    rp["it_off"] = np.stack([l["it_off"] + mv_off[c] for c, l in enumerate(logs)])
+    for k_ in ("mv_U", "mv_Uadj", "mv_u"):
+        rp[k_] = np.concatenate([l[k_] for l in logs])
+    states = {int(i): j for j, i in enumerate(g["state_iter"])}
+    ctx.set_state(np.stack([l["state_edges"][0] for l in logs]), np.stack([l["state_bits"][0] for l in logs]))
+    ctx.init_logl(kind)
+    it = 1
+    while it < M:
+        if it % R == 0:
+            j = states[it]
+            ctx.set_state(np.stack([l["state_edges"][j] for l in logs]), np.stack([l["state_bits"][j] for l in logs]))
+        end = min((it // R + 1) * R, M)
+        ctx.run(kind, it, end, replay=rp)
+        it = end
+    ctx.sync()
+    nprop_g, nacc_g = ctx.counts()
+    off, rec, bits = ctx.updates()
+    out = dict(n_prop=nprop_g, n_acc=nacc_g, logl=ctx.logl(), off=off, rec=rec, bits=bits, mlog=ctx.move_log(),
+               logs=logs)
+    ctx.close()
+    return out

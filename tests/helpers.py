@@ -18,7 +18,7 @@ def trajectory_fixtures():
     out = []
     for f in sorted(glob.glob(os.path.join(GOLD, "*.npz"))):
         n = os.path.basename(f)[:-4]
-        if n in ("scorers", "forest", "jt_counts"):
+        if n in ("scorers", "forest", "jt_counts") or n.startswith("batch_"):
             continue
         out.append(n)
     return out
@@ -44,3 +44,25 @@ def close(a, b, rtol=1e-9):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) <= rtol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+
+
+BATCH_FIXED = ("state_edges", "state_bits", "it_node", "it_mtype_raw", "it_aux", "it_off", "logl")
+BATCH_MV = ("mv_U", "mv_Uadj", "mv_u", "mv_dlik", "mv_dprior", "mv_logq")
+BATCH_UPD = ("upd_i", "upd_k", "upd_type", "upd_node", "upd_C", "upd_Cadj")
+
+
+def batch_chain_log(g, c):
+    """The replay log of chain c of a batch fixture (oracle/make_golden.py:loglin_batch), in the layout
+    of a single-chain fixture."""
+    log = {k: g[k] for k in ("model", "data", "levels", "cell_alpha", "prior", "p", "n_samples", "randomize",
+                             "single", "state_iter")}
+    for k in BATCH_FIXED:
+        log[k] = g[k][c]
+    a, b = int(g["mv_off"][c]), int(g["mv_off"][c + 1])
+    for k in BATCH_MV:
+        log[k] = g[k][a:b]
+    a, b = int(g["upd_off"][c]), int(g["upd_off"][c + 1])
+    for k in BATCH_UPD:
+        log[k] = g[k][a:b]
+    log["n_updates"] = g["n_updates"][c]
+    return log

@@ -53,6 +53,28 @@ def test_replay_bit_exact_vs_reference(name):
         assert close(out["logl"][c], g["logl"]).all()
 
 
+def test_replay_batch_of_distinct_reference_chains():
+    """Config 3 in miniature: 32 reference chains with different seeds (tiled to 128 chains of one
+    launch), every chain replaying its OWN reference log: bit-exact records, 1e-9 ratios."""
+    from tests import gpu_common as gc
+    g = load_golden("batch_cfg3_p15_parallel_32chains")
+    out = gc.run_gpu_replay_batch(g, reps=4)
+    for c, log in enumerate(out["logs"]):
+        assert out["n_prop"][c] == int(log["n_updates"])
+        r = out["rec"][out["off"][c]:out["off"][c + 1]]
+        b = out["bits"][out["off"][c]:out["off"][c + 1]]
+        assert np.array_equal(r["i"], log["upd_i"]) and np.array_equal(r["k"], log["upd_k"])
+        assert np.array_equal(r["type"].astype(np.int32), log["upd_type"])
+        assert np.array_equal(r["node"].astype(np.int32), log["upd_node"])
+        assert np.array_equal(b[:, 0], log["upd_C"]) and np.array_equal(b[:, 1], log["upd_Cadj"])
+        nprop = int(log["n_updates"])
+        ml = {f: out["mlog"][f][c, :nprop] for f in out["mlog"]}
+        assert np.array_equal(ml["U"], log["mv_U"]) and np.array_equal(ml["u"], log["mv_u"])
+        assert close(ml["dlik"], log["mv_dlik"]).all() and close(ml["dprior"], log["mv_dprior"]).all()
+        assert close(ml["logq"], log["mv_logq"]).all()
+        assert close(out["logl"][c], log["logl"]).all()
+
+
 PROD_CASES = [
     ("uniform7_parallel_s1", 0, 6, 600, 50),
     ("uniform7_single_s2", 1, 6, 600, 50),

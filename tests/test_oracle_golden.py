@@ -44,6 +44,28 @@ def test_replay_matches_reference(name):
     assert close(res["logl"], g["logl"]).all()
 
 
+def test_replay_batch_of_reference_chains():
+    """Config 3: 32 independent reference chains (seeds 100..131) on discrete_loglin_p15, every one
+    replayed through the oracle: bit-exact trajectories, 1e-9 log-acceptance terms."""
+    from tests.helpers import batch_chain_log
+    g = load_golden("batch_cfg3_p15_parallel_32chains")
+    m = oracle_model(g)
+    for c in range(len(g["n_updates"])):
+        log = batch_chain_log(g, c)
+        res = orc.run_replay(m, log)
+        assert res["rc"] == 0 and res["k"] == int(log["n_updates"])
+        r = res["recs"]
+        assert np.array_equal(r["i"], log["upd_i"]) and np.array_equal(r["k"], log["upd_k"])
+        assert np.array_equal(r["type"], log["upd_type"]) and np.array_equal(r["node"], log["upd_node"])
+        assert np.array_equal(res["rec_bits"][:, 0], log["upd_C"])
+        assert np.array_equal(res["rec_bits"][:, 1], log["upd_Cadj"])
+        mv = res["moves"]
+        assert np.array_equal(mv["U"], log["mv_U"]) and np.array_equal(mv["Uadj"], log["mv_Uadj"])
+        assert close(mv["dlik"], log["mv_dlik"]).all() and close(mv["dprior"], log["mv_dprior"]).all()
+        assert close(mv["logq"], log["mv_logq"]).all()
+        assert close(res["logl"], log["logl"]).all()
+
+
 def test_scorers_match_reference():
     g = load_golden("scorers")
     for tag, D, delta in (("I1", None, 1.0), ("I5", None, 5.0), ("G3", g["ggm_Dgen"], 3.0)):
