@@ -105,7 +105,17 @@ __device__ __forceinline__ bool ldl_logdets(double *a, int lane, int k, int ks, 
             for (; i < k; i += 32) {
                 const double f = a[tri(i, j)] * inv;
                 double *row = a + tri(i, 0);
-                for (int l = j + 1; l <= i; ++l) row[l] -= f * a[tri(l, j)];
+                // four elements at a time, loads before stores (row i and column j never overlap:
+                // l > j), same multiply-subtract per element
+                int l = j + 1, cj = tri(j + 1, j);
+                for (; l + 3 <= i; l += 4) {
+                    const double c0 = a[cj], c1 = a[cj + l + 1], c2 = a[cj + 2 * l + 3], c3 = a[cj + 3 * l + 6];
+                    double r0 = row[l], r1 = row[l + 1], r2 = row[l + 2], r3 = row[l + 3];
+                    r0 -= f * c0; r1 -= f * c1; r2 -= f * c2; r3 -= f * c3;
+                    row[l] = r0; row[l + 1] = r1; row[l + 2] = r2; row[l + 3] = r3;
+                    cj += 4 * l + 10;
+                }
+                for (; l <= i; ++l) { row[l] -= f * a[cj]; cj += l + 1; }
             }
         }
     }

@@ -260,10 +260,21 @@ __device__ __forceinline__ int build_index_sorted(const u64 (&X)[WMAX], int W, i
 __device__ __forceinline__ bool gather_ldl(const double *__restrict__ mat, int p, double *a, const short *idx,
                                            int lane, int k, double &logdet)
 {
-    for (int i = lane; i < k; i += 32) {
-        const double *row = mat + (size_t)idx[i] * p;
-        double *dst = a + tri(i, 0);
-        for (int l = 0; l <= i; ++l) dst[l] = __ldg(row + idx[l]);
+    if (k <= 32) {
+        // lane <-> column: one coalescing-free but INDEPENDENT load per lane and row (the row index
+        // comes by shuffle, so no shared-memory read sits between the loads and they pipeline)
+        const int mycol = (lane < k) ? (int)idx[lane] : 0;
+#pragma unroll 4
+        for (int i = 0; i < k; ++i) {
+            const int ri = __shfl_sync(PDG_FULL, mycol, i);
+            if (lane <= i) a[tri(i, lane)] = __ldg(mat + (size_t)ri * p + mycol);
+        }
+    } else {
+        for (int i = lane; i < k; i += 32) {
+            const double *row = mat + (size_t)idx[i] * p;
+            double *dst = a + tri(i, 0);
+            for (int l = 0; l <= i; ++l) dst[l] = __ldg(row + idx[l]);
+        }
     }
     double sS, ldv, lsc;
     return ldl_logdets(a, lane, k, 0, k, sS, logdet, ldv, lsc);

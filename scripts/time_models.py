@@ -6,8 +6,8 @@ import torch
 from paralleldg_b200 import _native as nat, engine, datagen, mh_parallel as mh
 from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
 
-p, n, C, M, R = int(sys.argv[1]) if len(sys.argv) > 1 else 50, 100, 1024, int(os.environ.get("TM_M", "2000")), 100
-X, _ = datagen.ggm_ar_data(p, n, 50)
+p, n, C, M, R = int(sys.argv[1]) if len(sys.argv) > 1 else 50, int(os.environ.get("TM_NG", "100")), 1024, int(os.environ.get("TM_M", "2000")), 100
+X, _ = datagen.ggm_ar_data(p, n, int(os.environ.get("TM_SEED", "50")))
 for name in sys.argv[2:] or ["uniform", "ggm"]:
     if name == "loglin":
         data, lv, _ = datagen.loglin_ar_data(p, int(os.environ.get("TM_N", "100000")), 100)
