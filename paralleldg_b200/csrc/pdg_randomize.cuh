@@ -10,7 +10,8 @@
 struct RandSmem {
     int off_card, off_order, off_cliqueof, off_parent, off_keys, off_jdraw, off_comp, off_nodes, off_rank,
         off_cstart, off_canon, off_compidx, off_vind, off_wj, off_cnt, off_fill, off_off, off_newe,
-        off_done, off_inT, off_inw, off_isroot, off_numbered, off_used, off_X, off_wmask, off_sepsz, off_deg32, total;
+        off_done, off_inT, off_inw, off_isroot, off_numbered, off_used, off_X, off_wmask, off_sepsz, off_deg32,
+        off_sets, total;      // off_sets < 0: adj / K / sep stay in the global scratch
 };
 
 __host__ __device__ inline RandSmem rand_smem_layout(int p, int W)
@@ -28,6 +29,9 @@ __host__ __device__ inline RandSmem rand_smem_layout(int p, int W)
     s.off_numbered = o; o += W * 8; s.off_used = o; o += W * 8; s.off_X = o; o += W * 8;
     s.off_wmask = o; o += a1; s.off_sepsz = o; o += a2;
     s.off_deg32 = o; o += ((p + 2) * 4 + 15) / 16 * 16;
+    // up to 128 vertices the three p x W work tables (graph adjacency, cliques, separators) live in
+    // shared memory too (<= 6 KB): the MCS walks them with one dependent access per step
+    if (p * W <= 256) { s.off_sets = o; o += 3 * p * W * 8; } else s.off_sets = -1;
     s.total = o;
     return s;
 }
@@ -158,6 +162,7 @@ __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long lon
     u64 *Mc = P.M + (size_t)chain * p * W;
     const u64 *Nc = P.N + (size_t)chain * p * W;
     u64 *adj = Z.adj + (size_t)chain * p * W, *K = Z.K + (size_t)chain * p * W, *sep = Z.sep + (size_t)chain * p * W;
+    if (L.off_sets >= 0) { adj = (u64 *)(smem + L.off_sets); K = adj + (size_t)p * W; sep = K + (size_t)p * W; }
     int *E = P.edges + (size_t)chain * 2 * (p - 1);
     const u32 gchain = P.chain0 + (u32)chain, k0 = P.seed_lo, k1 = P.seed_hi;
 
