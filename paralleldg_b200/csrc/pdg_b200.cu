@@ -229,6 +229,7 @@ struct pdg_ctx {
     int wmax = 1;                         // compile-time word count the kernels are dispatched on
     int wpc = 8;                          // warps (= chains) per CTA of the MH kernel (8 -> one CTA per SM at 1024 chains)
     bool smem_state = false;
+    bool light = false;                   // log-linear model with few rows: the 128-register MH kernel
     int memo_bits = 24;
     // compaction
     long long *d_offsets = nullptr;
@@ -286,15 +287,15 @@ static int set_smem(pdg_ctx *ctx, F f, int bytes)
     return PDG_OK;
 }
 
-template <int MODEL, int WMAX, bool SS>
-static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
+template <int MODEL, int WMAX, bool SS, bool LIGHT>
+static int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
     const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
     const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
     const int per_warp = (randomize > 0 && LR.total > L.total) ? LR.total : L.total;
     const int wpc = ctx->wpc, sm = per_warp * wpc;
     int rc;
-    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS>, sm))) return rc;
+    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT>, sm))) return rc;
     const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
     time_begin(ctx, ctx->ev_run);
     // chains of one CTA re-align every `lockstep` iterations (power of two, 0 = never)
@@ -306,11 +307,20 @@ static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const 
         if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
         if (lockstep & (lockstep - 1)) lockstep = 0;
     }
-    k_mh_run<MODEL, WMAX, SS><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
+    k_mh_run<MODEL, WMAX, SS, LIGHT><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
     time_end(ctx, ctx->ev_run);
     ctx->launches++;
     CK(cudaGetLastError());
     return PDG_OK;
+}
+
+template <int MODEL, int WMAX, bool SS>
+static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
+{
+    if constexpr (MODEL == PDG_MODEL_LOGLIN) {
+        if (ctx->light) return launch_run_k<MODEL, WMAX, SS, true>(ctx, kind, b, e, R, randomize);
+    }
+    return launch_run_k<MODEL, WMAX, SS, false>(ctx, kind, b, e, R, randomize);
 }
 
 template <int MODEL, int WMAX>
@@ -651,8 +661,11 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     P.n_ktab = n_ktab; P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
     P.hist = (unsigned int *)d_hist; P.hist_cells = hist_cells; P.sp = sp;
     P.model = PDG_MODEL_LOGLIN;
+    // few rows: a scan is cheap, so the light kernel (two CTAs per SM, 1024-cell tables) runs the chains
+    ctx->light = nrows <= 8192;
+    if (const char *v = getenv("PDG_LIGHT")) ctx->light = atoi(v) != 0;
     // per-warp shared count table: 4096 cells when a CTA of the MH kernel still fits in shared memory
-    P.ll_cap = 4096;
+    P.ll_cap = ctx->light ? 1024 : 4096;
     if (const char *v = getenv("PDG_LL_CAP")) { const int x = atoi(v); if (x >= 1024 && x <= 8192 && !(x & (x - 1))) P.ll_cap = x; }
     for (;;) {
         const RunSmem L = run_smem_layout(P.p, P.W, ctx->smem_state, tri_bytes_for(P.ll_cap));

@@ -49,18 +49,19 @@ __device__ __forceinline__ void ll_red_shared(unsigned int addr)
     asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
 }
 
-template <int MODE, bool GLB>
+// NB = 512-row blocks per warp pass (4: 16 loads in flight per lane; 1 for the light MH kernel)
+template <int MODE, bool GLB, int NB>
 __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long long ld, long long n, LlCount q,
                                                    const unsigned int *colinfo, int lane)
 {
     constexpr int NC = MODE == 0 ? 1 : 2;
-    uint4 x[4][4];
+    uint4 x[4][NB];
     auto issue = [&](long long base, int j0) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const unsigned char *col = D + (size_t)colinfo[16 + j0 + jj] * (size_t)ld + base + lane * 16;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[jj][u] = __ldg((const uint4 *)(col + 512 * u));
+            for (int u = 0; u < NB; ++u) x[jj][u] = __ldg((const uint4 *)(col + 512 * u));
         }
     };
     // a, b: this row's codeA / codeB (MODE 1) or the code and nothing (MODE 0, 2)
@@ -72,10 +73,10 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
         }
     };
     issue(0, 0);
-    for (long long base = 0; base < n; base += 2048) {
-        unsigned int c[4][4][NC];
+    for (long long base = 0; base < n; base += 512 * NB) {
+        unsigned int c[NB][4][NC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < NB; ++u)
 #pragma unroll
             for (int w = 0; w < 4; ++w)
 #pragma unroll
@@ -88,7 +89,7 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NB; ++u) {
                     const unsigned int w4[4] = {x[jj][u].x, x[jj][u].y, x[jj][u].z, x[jj][u].w};
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
@@ -105,11 +106,11 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
                 }
             }
             const int nj0 = (j0 + 4 < q.nslots) ? j0 + 4 : 0;
-            const long long nbase = nj0 ? base : base + 2048;
+            const long long nbase = nj0 ? base : base + 512 * NB;
             if (nbase < n) issue(nbase, nj0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NB; ++u) {
             const long long r = base + 512 * u + lane * 16;
             if (r < ld) {      // ld is a multiple of 16: the padding rows land in cell 0 and are subtracted by the caller
 #pragma unroll
@@ -207,7 +208,7 @@ __device__ __forceinline__ double loglin_derive(const LoglinArgs &P, const WarpS
     return sc;
 }
 
-template <int WMAX>
+template <int WMAX, int NB>
 __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane, LlTable &tout)
 {
     ScoreRes res; res.score = 0.0; res.err = 0;
@@ -267,11 +268,11 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
         q.sbase = (unsigned int)__cvta_generic_to_shared(sh) + 4u * (unsigned int)(lane & (R - 1));
         if (glb) { q.mulA = mode == 1 ? prodB : 1u; q.mulB = 1u; }
         else { q.mulB = 4u << rshift; q.mulA = mode == 1 ? prodB * q.mulB : q.mulB; }
-        if (mode == 0) loglin_count_dense<0, false>(D, P.ld, n, q, colinfo, lane);
-        else if (mode == 1 && !glb) loglin_count_dense<1, false>(D, P.ld, n, q, colinfo, lane);
-        else if (mode == 1) loglin_count_dense<1, true>(D, P.ld, n, q, colinfo, lane);
-        else if (!glb) loglin_count_dense<2, false>(D, P.ld, n, q, colinfo, lane);
-        else loglin_count_dense<2, true>(D, P.ld, n, q, colinfo, lane);
+        if (mode == 0) loglin_count_dense<0, false, NB>(D, P.ld, n, q, colinfo, lane);
+        else if (mode == 1 && !glb) loglin_count_dense<1, false, NB>(D, P.ld, n, q, colinfo, lane);
+        else if (mode == 1) loglin_count_dense<1, true, NB>(D, P.ld, n, q, colinfo, lane);
+        else if (!glb) loglin_count_dense<2, false, NB>(D, P.ld, n, q, colinfo, lane);
+        else loglin_count_dense<2, true, NB>(D, P.ld, n, q, colinfo, lane);
         __syncwarp();
         if (!glb) {
             // fold the replicas into a compact table sh[0 .. Ki) (32 cells at a time: all reads of a
@@ -374,14 +375,14 @@ __device__ __forceinline__ LoglinArgs loglin_args(const PdgParams &P)
     return A;
 }
 
-template <int WMAX>
+template <int WMAX, int NB>
 __device__ __forceinline__ int loglin_set_score(const PdgParams &P, const WarpScratch &ws, int slot,
                                                 const u64 (&X)[WMAX], int lane, double &score, LlTable &t)
 {
     KeyW<WMAX> K;
 #pragma unroll
     for (int w = 0; w < WMAX; ++w) K.w[w] = X[w];
-    const ScoreRes r = loglin_scan<WMAX>(loglin_args(P), ws, slot, K, lane, t);
+    const ScoreRes r = loglin_scan<WMAX, NB>(loglin_args(P), ws, slot, K, lane, t);
     score = r.score;
     return r.err;
 }

@@ -71,7 +71,7 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state
 //   otherwise          : memo table; the warp resolves the misses one after the other with the
 //                        cooperative scorers (32-row LDL^T / contingency-table scan)
 // Returns the ERR_* bits raised.
-template <int MODEL, int WMAX>
+template <int MODEL, int WMAX, int NB = 4>
 __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
                                            int lane, const u64 (&X)[WMAX], bool need, double &score,
                                            unsigned long long (&wk)[8])
@@ -123,7 +123,7 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
         int e;
         LlTable tab; tab.cells = 0u; tab.k = 0;
         if (MODEL == PDG_MODEL_GGM) e = ggm_set_score<WMAX>(P, ws, Y, lane, sc);
-        else e = loglin_set_score<WMAX>(P, ws, slot, Y, lane, sc, tab);
+        else e = loglin_set_score<WMAX, NB>(P, ws, slot, Y, lane, sc, tab);
         err |= e;
         if (lane == 0) {
             if (!e) memo_insert<WMAX>(P.memo, Y, W, sc);
@@ -168,8 +168,10 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     return err;
 }
 
-template <int MODEL, int WMAX, bool SMEM_STATE>
-__global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long it_begin, long long it_end,
+// LIGHT (log-linear models with few rows): one 512-row block per scan pass and a 128-register budget,
+// so that two CTAs (16 chains) share an SM when a GPU runs more than 1184 chains
+template <int MODEL, int WMAX, bool SMEM_STATE, bool LIGHT = false>
+__global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int kind, long long it_begin, long long it_end,
                                                 PdgReplayDev R, int lockstep, RandScratch Z, long long randomize, int smem_per_warp)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(256) k_mh_run(PdgParams P, int kind, long long
             double sc = 0.0;
             if (MODEL != PDG_MODEL_UNIFORM) {
                 const int kq = (q == 0) ? kb : (q == 1) ? ks : (q == 2) ? kb + 1 : ks + 1;
-                errflag |= warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, wk);
+                errflag |= warp_scores<MODEL, WMAX, LIGHT ? 1 : 4>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, wk);
             }
             PT(4)
             const double sc1 = __shfl_down_sync(PDG_FULL, sc, 1), sc2 = __shfl_down_sync(PDG_FULL, sc, 2),
