@@ -185,6 +185,17 @@ def test_loglin_scorer_matches_reference():
     assert close(got, g["ll_l3_score_a2"], 1e-11).all()
 
 
+@pytest.mark.parametrize("env", [{"PDG_LIGHT": "0"}, {"PDG_LIGHT": "1"}, {"PDG_FUSED": "1"}, {"PDG_FUSED": "0", "PDG_LOCKSTEP": "0"},
+                                 {"PDG_LL_CAP": "1024", "PDG_LIGHT": "0"}, {"PDG_WPC": "3"}])
+def test_kernel_variants_give_identical_chains(monkeypatch, env):
+    """The light / regular log-linear kernels, fused / per-launch randomisation, the re-alignment barrier,
+    the shared count-table size and the CTA width are performance knobs: same chains, bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_production_mode_matches_oracle("cfg3_p15_parallel_s0", 0, 11, 600, 100)
+    test_production_mode_matches_oracle("cfg1_czech_single_s1", 1, 5, 500, 100)
+
+
 def test_loglin_sparse_cell_path_equals_dense(monkeypatch):
     """sets with more cells than the dense per-warp table go through the hashed-cell pool"""
     from paralleldg_b200 import engine
