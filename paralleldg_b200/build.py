@@ -30,6 +30,8 @@ def build_native(force=False, verbose=False):
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if os.environ.get("PDG_LANE_SMEM"):
         cmd.insert(1, "-DPDG_LANE_SMEM")
+    if os.environ.get("PDG_NO_K4"):
+        cmd.insert(1, "-DPDG_NO_K4=1")
     if os.environ.get("PDG_PHASE_TIMERS"):
         cmd.insert(1, "-DPDG_PHASE_TIMERS")
     if verbose:

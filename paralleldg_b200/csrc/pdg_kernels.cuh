@@ -386,6 +386,10 @@ __device__ unsigned long long g_pt[8];
 #define LPT(i)
 #endif
 
+#ifndef PDG_NO_K4
+#define PDG_NO_K4 0
+#endif
+
 template <int K, int WMAX>
 __device__ __forceinline__ int ggm_lane_score_k(const PdgParams &P, const LaneScratch &ls, int lane, const u64 (&X)[WMAX], int k,
                                                 double &score)
@@ -480,7 +484,7 @@ __device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const LaneScr
 #endif
     const int kmax = (int)__reduce_max_sync(PDG_FULL, (unsigned)k);
     if (kmax == 0) { score = 0.0; return 0; }
-    if (kmax <= 4) return ggm_lane_score_k<4, WMAX>(P, ls, lane, X, k, score);
+    if (kmax <= 4 && !PDG_NO_K4) return ggm_lane_score_k<4, WMAX>(P, ls, lane, X, k, score);
     if (kmax <= 8) return ggm_lane_score_k<8, WMAX>(P, ls, lane, X, k, score);
     return ggm_lane_score_k<12, WMAX>(P, ls, lane, X, k, score);
 }
