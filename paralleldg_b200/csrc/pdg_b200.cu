@@ -184,6 +184,10 @@ __global__ void k_memo_clear(MemoTable T)
         if (T.W == 1) T.kv[i] = make_ulonglong2(0ull, MEMO_SENT);
         else { T.tag[i] = 0ull; T.val[i] = MEMO_SENT; }
     }
+    // multi-word keys: the key words are cleared as well.  A writer that finds its own tag in a slot
+    // publishes a value there once the key words match; with words left over from an earlier run
+    // (and two keys sharing a tag) that match could be against a key the slot no longer holds.
+    if (T.W > 1) for (size_t i = i0; i < n * (size_t)T.W; i += st) T.keyw[i] = 0ull;
 }
 
 // trajectory compaction: exclusive scan of the per-chain record counts, then a packed copy

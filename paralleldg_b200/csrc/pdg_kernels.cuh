@@ -128,12 +128,14 @@ __device__ __forceinline__ u64 mix64(u64 k)
 template <int WMAX>
 __device__ __forceinline__ u64 key_hash(const u64 (&X)[WMAX], int W)
 {
-    // multilinear combination of the words (independent multiplies, odd multipliers), one finaliser:
-    // a serial mix64 per word was 6 % of the p = 500 kernel
+    // multilinear combination of the words (independent multiplies by unrelated odd constants), one
+    // finaliser: a serial mix64 per word was 6 % of the p = 500 kernel.  (Multipliers in arithmetic
+    // progression would let structured bitsets collide: sum(d_w) = sum(w d_w) = 0.)
+    const u64 MUL[8] = {0xBF58476D1CE4E5B9ull, 0x94D049BB133111EBull, 0xD6E8FEB86659FD93ull, 0xFF51AFD7ED558CCDull,
+                        0xC4CEB9FE1A85EC53ull, 0x9FB21C651E98DF25ull, 0xE7037ED1A0B428DBull, 0xA0761D6478BD642Full};
     u64 h = 0x9E3779B97F4A7C15ull;
 #pragma unroll
-    for (int w = 0; w < WMAX; ++w)
-        if (w < W) h += (X[w] ^ (0xD6E8FEB86659FD93ull * (u64)(w + 1))) * (0xBF58476D1CE4E5B9ull + 0x94D049BB133111EAull * (u64)w);
+    for (int w = 0; w < WMAX; ++w) if (w < W) h += (X[w] + 0x2545F4914F6CDD1Dull * (u64)(w + 1)) * MUL[w & 7];
     return mix64(h);
 }
 

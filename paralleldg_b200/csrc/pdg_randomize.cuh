@@ -71,6 +71,7 @@ __device__ __forceinline__ void build_derived(const PT &P, long long chain, int 
     unsigned short *g_adj = P.csr_adj + (size_t)chain * 2 * p;
     for (int i = lane; i < p * W; i += 32) Nc[i] = 0ull;
     for (int i = lane; i <= p; i += 32) s_deg[i] = 0;
+    __threadfence();
     __syncwarp();
     for (int i0 = lane; i0 < p * W; i0 += 128) {
         u64 xs[4];                                   // four independent loads in flight per lane
@@ -108,6 +109,7 @@ __device__ __forceinline__ void build_derived(const PT &P, long long chain, int 
         g_adj[atomicAdd(&s_deg[a], 1)] = (unsigned short)b;
         g_adj[atomicAdd(&s_deg[b], 1)] = (unsigned short)a;
     }
+    __threadfence();              // N (atomic ORs) and the CSR are read back by other lanes right after
     __syncwarp();
 }
 
@@ -242,6 +244,7 @@ __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long lon
         for (int i = lane; i < p * W; i += 32) { adj[i] = 0ull; K[i] = 0ull; sep[i] = 0ull; }
         for (int i = lane; i < p; i += 32) { done[i] = 0; inT[i] = 0; }
         if (lane < W) { numbered[lane] = 0ull; used[lane] = 0ull; }
+        __threadfence();          // the zeroes must be in L2 before another lane's OR reaches the same word
         __syncwarp();
         for (int t = lane; t < p; t += 32) {
             u64 c[8];
@@ -258,6 +261,7 @@ __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long lon
                 }
             }
         }
+        __threadfence();          // fire-and-forget reductions: performed before any lane reads a row back
         __syncwarp();
 
         // ---- (b) maximum cardinality search -> cliques K[0..S), parent[], sep[] ----------------

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
             __syncwarp();
             if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
             __syncwarp();
+            if (!SMEM_STATE) __threadfence();       // rows flipped with L2 atomics: nothing stale in L1 for the randomiser's loads
             randomize_chain(rand_args(P), Z, chain, (u32)it, smem, lane);
             __syncwarp();
             for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
             node = (int)__umulhi(r[0], (u32)p);
             mtype = (int)(r[1] >> 31);
         }
-        if (lane < W) s_sub[lane] = Nc[(size_t)node * W + lane];
+        // (state in global memory is updated with atomics in L2: read it there, never through L1)
+        if (lane < W) s_sub[lane] = SMEM_STATE ? Nc[(size_t)node * W + lane] : __ldcg(&Nc[(size_t)node * W + lane]);
         __syncwarp();
         int msub = 0;
 #pragma unroll
@@ -450,8 +452,8 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
             int kb = 0, ks = 0;
 #pragma unroll
             for (int w = 0; w < WMAX; ++w) {
-                Cw[w] = (valid && w < W) ? Mc[(size_t)U * W + w] : 0ull;
-                Aw[w] = (valid && adj && w < W) ? Mc[(size_t)Ua * W + w] : 0ull;
+                Cw[w] = (valid && w < W) ? (SMEM_STATE ? Mc[(size_t)U * W + w] : __ldcg(&Mc[(size_t)U * W + w])) : 0ull;
+                Aw[w] = (valid && adj && w < W) ? (SMEM_STATE ? Mc[(size_t)Ua * W + w] : __ldcg(&Mc[(size_t)Ua * W + w])) : 0ull;
                 const u64 vb = ((node >> 6) == w) ? (1ull << (node & 63)) : 0ull;
                 const u64 B = Cw[w] & ~vb, S0 = B & Aw[w];
                 kb += __popcll(B); ks += __popcll(S0);
@@ -527,6 +529,7 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
                 atomicXor(&Mc[(size_t)U * W + (node >> 6)], 1ull << (node & 63));
                 atomicXor(&Nc[(size_t)node * W + (U >> 6)], 1ull << (U & 63));
             }
+            if (!SMEM_STATE && am) __threadfence();         // the bit flips are performed before any lane reads the rows again
             __syncwarp();
         }
         PT(6)

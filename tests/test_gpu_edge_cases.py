@@ -170,3 +170,36 @@ def test_full_size_config2_properties():
     i, j = np.indices(marg.shape)
     near, far = marg[(np.abs(i - j) <= 5) & (i != j)], marg[np.abs(i - j) > 5]
     assert near.mean() > 3 * far.mean(), (near.mean(), far.mean())
+
+
+def test_large_p_runs_are_reproducible_and_match_oracle():
+    """Config 4 in miniature (p = 500, state in global memory, 8-word memo keys, cooperative scorer):
+    the same seeded run three times gives identical chains (the memo table and the L2-resident state are
+    shared by concurrently running warps: a race shows up as run-to-run differences), and a subset of the
+    chains equals the CPU oracle bit for bit."""
+    from paralleldg_b200 import datagen, engine, mh_parallel as mh
+    from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
+    p, n, C, M, R, seed = 500, 1000, 1024, 3000, 100, 20261019
+    X, _ = datagen.ggm_ar_data(p, n, 500)
+    sd = seqdist.GGMJTPosterior()
+    sd.init_model(X, np.identity(p), 1.0, {})
+    ctx = engine.make_context(sd, mh.get_prior(["mbc", 2.0, 4.0]), C, M, seed=seed, rec_cap=M)
+    runs = []
+    for rep in range(3):
+        ctx.set_cliques(None)
+        ctx.randomize(0)
+        ctx.sample(0, R)
+        ctx.sync()
+        runs.append((ctx.counts()[0].copy(), ctx.logl().copy(), ctx.get_state()[1].copy()))
+    ctx.close()
+    for rep in (1, 2):
+        assert np.array_equal(runs[rep][0], runs[0][0])
+        assert np.array_equal(runs[rep][1], runs[0][1])
+        assert np.array_equal(runs[rep][2], runs[0][2])
+    m = orc.Model.ggm(X, None, 1.0)
+    Co = 64
+    o = orc.run_many(m, 0, Co, M, R, seed, chain0=0, n_threads=8, want_logl=True, rec_cap=4 * M, want_state=True)
+    assert o["rc"] == 0
+    assert np.array_equal(runs[0][0][:Co], o["n_prop"])
+    assert np.array_equal(runs[0][2][:Co], o["final_bits"])
+    assert close(runs[0][1][:Co], o["logl"]).all()
