@@ -156,6 +156,8 @@ int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies);
  * for the complete sets actually EVALUATED (memo misses): work[0] = bytes (GGM 8 k^2, log-linear
  * n k per set), work[1] = 6 x flops (GGM 2k^3 + 3k^2 + 6k per set), work[2] = sets, work[3] = sum
  * of k; for the sets REQUESTED by proposals (hits + misses): work[4] = sets, work[5] = sum of k;
+ * work[6] = log-linear sets counted through the hashed-cell pool, work[7] = log-linear sets whose
+ * score was read off the count table of a superset scanned in the same pass;
  * work[8..15] = developer phase timers (zero unless built with -DPDG_PHASE_TIMERS) */
 int pdg_enable_timing(pdg_ctx *ctx, int on);
 int pdg_get_timing(pdg_ctx *ctx, double *ms_run, double *ms_randomize, int64_t *n_run, int64_t *n_randomize);
