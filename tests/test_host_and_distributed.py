@@ -151,3 +151,25 @@ def test_world_size_2_reduction_and_gather_over_gloo():
     assert nch == 5 and props == [10, 11, 12, 13, 14]
     assert offs == [0, 0, 1, 3, 6, 10]
     assert rec_i == [1, 2, 2, 3, 3, 3, 4, 4, 4, 4]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port timed on the host cores) prints ONE JSON line with the
+    keys of the bench contract, on the default workload's metric / unit / config."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mh_proposals_per_sec" and d["unit"] == "proposals/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["config"]["workload"] == "ggm_ar_p50_n100_M10000_R100_c1024"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["unit"] == d["unit"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
