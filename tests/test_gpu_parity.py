@@ -196,6 +196,34 @@ def test_kernel_variants_give_identical_chains(monkeypatch, env):
     test_production_mode_matches_oracle("cfg1_czech_single_s1", 1, 5, 500, 100)
 
 
+def test_loglin_subset_scores_read_off_superset_tables():
+    """Supersets and their subsets missing together in one 32-set scoring pass: the subsets are marginalised
+    out of the superset's count table instead of being scanned -- same bits as the oracle's own counts
+    (binary and 3-level data, tables with one and with two packed column groups)."""
+    import itertools
+    from paralleldg_b200 import engine
+    g = load_golden("scorers")
+    rng = np.random.RandomState(7)
+    for tag, alpha in (("p15", 1.0), ("l3", 2.0)):
+        data, levels = g["ll_%s_data" % tag], g["ll_%s_levels" % tag]
+        p = data.shape[1]
+        m = orc.Model.loglin(data, levels, alpha)
+        ctx = engine.scorer_for(_loglin_sd(data, levels, alpha)).ctx
+        for k in sorted(set(min(p, k_) for k_ in (3, 5, 9, 10))):
+            top = sorted(rng.choice(p, k, replace=False).tolist())
+            subs = [top]
+            for r in range(k - 1, 0, -1):
+                subs += [list(c) for c in itertools.islice(itertools.combinations(top, r), 6)]
+            subs = subs[:32]                      # one pass of the batch scorer: largest first, then its subsets
+            bits = np.zeros((len(subs), ctx.W), np.uint64)
+            for i, ss in enumerate(subs):
+                for v in ss:
+                    bits[i, v >> 6] |= np.uint64(1) << np.uint64(v & 63)
+            got = ctx.score_sets(bits)
+            want = np.array([m.score(b) for b in bits])
+            assert close(got, want, 1e-11).all(), (tag, k, np.abs(got - want).max())
+
+
 def test_loglin_sparse_cell_path_equals_dense(monkeypatch):
     """sets with more cells than the dense per-warp table go through the hashed-cell pool"""
     from paralleldg_b200 import engine
