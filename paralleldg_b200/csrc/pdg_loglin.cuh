@@ -9,9 +9,10 @@
 #pragma once
 #include "pdg_kernels.cuh"
 
-// Everything the scan needs, by value: the function below is deliberately OUT OF LINE (its own
-// register allocation -- the unrolled loads would otherwise spill the MH kernel -- and no address
-// of the kernel parameter block is taken).
+// Everything the scan needs, by value, so that no address of the kernel parameter block is taken
+// (that would move the whole block to local memory).  The scan is inlined into its callers: as an
+// out-of-line function its by-value arguments went through a 320-byte stack frame and the kernel
+// kept 255 registers anyway.
 struct LoglinArgs {
     const unsigned char *data; const int *levels; long long nrows, ld; int zero_col; double cell_alpha;
     int n_ktab; const double *ktab, *alphatab, *lgtab;
