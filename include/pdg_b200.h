@@ -168,6 +168,14 @@ int pdg_get_work(pdg_ctx *ctx, int64_t work[16]);
 int pdg_host_alloc(void **ptr, int64_t bytes);
 int pdg_host_free(void *ptr);
 
+/* machine ceilings for the roofline of the scoring kernels, measured on `device` (bench.py):
+ * fp64 DFMA throughput (GFLOP/s) for the log-det path (wishart.py:17-37); L2-resident and HBM read
+ * bandwidth (GB/s) and shared-memory reduction rates (G reductions/s) for the contingency-table
+ * scans (auxiliary_functions.py:134-151).  Not tied to a context. */
+enum pdg_probe_kind { PDG_PROBE_FP64 = 0, PDG_PROBE_L2_READ = 1, PDG_PROBE_HBM_READ = 2,
+                      PDG_PROBE_RED_SHARED_FREE = 3, PDG_PROBE_RED_SHARED_RANDOM = 4 };
+int pdg_probe(int device, int which, double *out);
+
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pdg_launch_count(pdg_ctx *ctx);
 

@@ -296,6 +296,91 @@ def jt_count_fixture(ref):
     save("jt_counts", **out)
 
 
+def loglin_batch_compact(ref, name, data, n_levels, kind, M, R, seeds, with_terms=True, prior=("mbc", 2.0, 4.0), pseudo_obs=1.0):
+    """Config 3 at scale: many reference chains in one fixture, narrow dtypes (tests/helpers.py:
+    expand_compact_batch restores the layout of loglin_batch).  p <= 64, < 128 tree nodes."""
+    levels = np.array([range(l) for l in n_levels])
+    logs = []
+    for seed in seeds:
+        sd = ref.seqdist.LogLinearJTPosterior()
+        sd.init_model(np.asarray(data), pseudo_obs, levels, {}, {})
+        sdg = ref.mh.get_prior(list(prior))
+        log, traj = rs.trace_chain(kind, M, R, sd, sdg, seed=seed)
+        logs.append(log)
+    l0 = logs[0]
+    out = dict(state_edges=np.stack([l["state_edges"] for l in logs]).astype(np.int8),
+               state_bits=np.stack([l["state_bits"] for l in logs]).astype(np.uint64),
+               it_node=np.stack([l["it_node"] for l in logs]).astype(np.int8),
+               it_mtype_raw=np.stack([l["it_mtype_raw"] for l in logs]).astype(np.int8),
+               it_aux=np.stack([l["it_aux"] for l in logs]).astype(np.int8),
+               it_cnt=np.stack([np.diff(l["it_off"]) for l in logs]).astype(np.uint8),
+               logl=np.stack([l["logl"] for l in logs]))
+    for k_, dt in (("mv_U", np.int8), ("mv_Uadj", np.int8), ("mv_u", np.float64)):
+        out[k_] = np.concatenate([l[k_] for l in logs]).astype(dt)
+    if with_terms:
+        for k_ in ("mv_dlik", "mv_dprior", "mv_logq"):
+            out[k_] = np.concatenate([l[k_] for l in logs])
+    for k_, dt in (("upd_i", np.int32), ("upd_k", np.int32), ("upd_type", np.int8), ("upd_node", np.int8),
+                   ("upd_C", np.uint64), ("upd_Cadj", np.uint64)):
+        out[k_] = np.concatenate([l[k_] for l in logs]).astype(dt)
+    out["upd_cnt"] = np.array([len(l["upd_i"]) for l in logs], dtype=np.int64)
+    out["n_updates"] = np.array([int(l["n_updates"]) for l in logs], dtype=np.int64)
+    save(name, compact=np.int32(1), model=np.array("loglin"), data=np.asarray(data, dtype=np.uint8),
+         levels=np.asarray(n_levels, dtype=np.int32), cell_alpha=np.float64(pseudo_obs), prior=prior_arr(prior),
+         p=l0["p"], n_samples=l0["n_samples"], randomize=l0["randomize"], single=l0["single"],
+         state_iter=l0["state_iter"], seeds=np.asarray(list(seeds), dtype=np.int64), **out)
+
+
+def czech_posterior_fixture(ref):
+    """(1) pooled posterior edge marginals of 96 independent REFERENCE chains on the czech data
+    (north_star: 'posterior edge marginals ... statistically consistent with the reference'), through
+    the reference's own Trajectory.empirical_distribution(burnin).heatmap() (trajectory.py:166-174,
+    empirical_graph_distribution.py:35-41); (2) for ONE traced chain the reference's own heat map,
+    graph-size series (trajectory.py:202-211) and benchpress CSVs (trajectory.py:232-370,
+    auxiliary_functions.py:381-403), next to its replay log."""
+    import contextlib
+    import io
+    import tempfile
+    rs.postprocess_shims()
+    import parallelDG.auxiliary_functions as aux
+    df = pd.read_csv(os.path.join(REFDATA, "czech_autoworkers.csv"), sep=",", header=[0, 1])
+    nl = np.array(df.columns.get_level_values(1), dtype=int)
+    labels = np.array(df.columns.get_level_values(0))
+    levels = np.array([range(l) for l in nl])
+    M, R, burnin, nch = 10000, 100, 2000, 96
+    heat = []
+    sizes = []
+    for c in range(nch):
+        sd = ref.seqdist.LogLinearJTPosterior()
+        sd.init_model(df.to_numpy(), 1.0, levels, {}, {})
+        sdg = ref.mh.get_prior(["mbc", 2.0, 4.0])
+        traj = rs.run_chain("parallel", M, R, sd, sdg, seed=5000 + c)
+        with contextlib.redirect_stdout(io.StringIO()):
+            heat.append(np.asarray(traj.empirical_distribution(burnin).heatmap(), dtype=np.float64))
+            sizes.append(np.asarray(traj.size(0), dtype=np.float64)[burnin:].mean())
+    heat = np.stack(heat)
+    out = dict(data=df.to_numpy().astype(np.uint8), levels=nl.astype(np.int32), labels=labels.astype(str),
+               n_samples=np.int32(M), randomize=np.int32(R), burnin=np.int32(burnin),
+               chain_heatmaps=heat, pooled=heat.mean(axis=0), mean_size=np.array(sizes))
+    # one traced chain with the reference's own post-processing
+    sd = ref.seqdist.LogLinearJTPosterior()
+    sd.init_model(df.to_numpy(), 1.0, levels, {}, {})
+    sdg = ref.mh.get_prior(["mbc", 2.0, 4.0])
+    log, traj = rs.trace_chain("parallel", 3000, 100, sd, sdg, seed=77)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["one_heatmap_b0"] = np.asarray(traj.empirical_distribution(0).heatmap(), dtype=np.float64)
+        traj.trajectory = None
+        out["one_heatmap_b500"] = np.asarray(traj.empirical_distribution(500).heatmap(), dtype=np.float64)
+        out["one_size"] = np.asarray(traj.size(0), dtype=np.float64)
+        d = tempfile.mkdtemp()
+        aux.write_traj_to_file(traj, d, labels=labels, output_filename="t.csv", output_format="benchpress")
+    out["one_csv_main"] = np.array(open(os.path.join(d, "t.csv")).read())
+    out["one_csv_sub"] = np.array(open(os.path.join(d, "t_subindex.csv")).read())
+    for k_, v in log.items():
+        out["one_" + k_] = v
+    save("czech_posterior", **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = rs.load_reference()
@@ -330,6 +415,22 @@ def main():
         df = pd.read_csv(os.path.join(REFDATA, "discrete_loglin_p15.csv"), sep=",", header=[0, 1])
         nl = np.array(df.columns.get_level_values(1), dtype=int)
         loglin_batch(ref, "batch_cfg3_p15_parallel_32chains", df.to_numpy(), nl, "parallel", 1000, 100, range(100, 132))
+    if want("p15scale"):
+        # config 3 at scale: 256 distinct reference chains at M=1000, 64 at the full M=10000
+        df = pd.read_csv(os.path.join(REFDATA, "discrete_loglin_p15.csv"), sep=",", header=[0, 1])
+        nl = np.array(df.columns.get_level_values(1), dtype=int)
+        loglin_batch_compact(ref, "batch_cfg3_p15_parallel_256chains_M1000", df.to_numpy(), nl, "parallel", 1000, 100,
+                             range(1000, 1256), with_terms=True)
+        loglin_batch_compact(ref, "batch_cfg3_p15_parallel_64chains_M10000", df.to_numpy(), nl, "parallel", 10000, 100,
+                             range(2000, 2064), with_terms=False)
+    if want("p62"):
+        # the largest binary p the reference's alpha rule can run (int64 product of levels)
+        sys.path.insert(0, ROOT)
+        from paralleldg_b200 import datagen
+        data, lv, adj = datagen.loglin_ar_data(62, 6000, seed=62)
+        loglin_case(ref, "loglin62_parallel_s1", data, lv, "parallel", 1500, 100, 1)
+    if want("czech_posterior"):
+        czech_posterior_fixture(ref)
     if want("ggm50"):
         # config 2: the CLI reads the CSV with header=0, so n = 99 (bin/parallelDG_ggm_sample:21)
         df = pd.read_csv(os.path.join(REFDATA, "AR1-5_p_50_sigma2_1.0_rho_0.9_n_100.csv"))

@@ -401,3 +401,46 @@ def trace_chain(kind, n_samples, randomize, sd, sd_graph, seed, init_graph=None)
         upd_Cnew=upd_Cnew, upd_C=upd_C, upd_Cadj=upd_Cadj,
     )
     return log, traj
+
+
+def postprocess_shims():
+    """Shims for the reference's OUTPUT code (trajectory.py:126-370, empirical_graph_distribution.py,
+    graph/graph.py:86-95), which uses pandas / networkx / numpy calls removed upstream.
+    Each restores the removed call with its documented behaviour; none touches the algorithm."""
+    import networkx as nx
+    import pandas as pd
+    if not hasattr(nx, "to_numpy_matrix"):
+        nx.to_numpy_matrix = lambda g, *a, **k: np.matrix(nx.to_numpy_array(g, *a, **k))
+    if not hasattr(pd.DataFrame, "append"):
+        pd.DataFrame.append = lambda self, other, **k: pd.concat([self, other], **k)
+    if not getattr(pd.Series.fillna, "_pdg_shim", False):
+        _orig = pd.Series.fillna
+
+        def fillna(self, value=None, method=None, **k):
+            if method == "ffill":
+                return self.ffill()
+            if method == "bfill":
+                return self.bfill()
+            return _orig(self, value, **k)
+        fillna._pdg_shim = True
+        pd.Series.fillna = fillna
+    if not hasattr(np, "float"):
+        np.float = float
+    if not hasattr(np, "float_"):
+        np.float_ = np.float64
+
+
+def run_chain(kind, n_samples, randomize, sd, sd_graph, seed, init_graph=None):
+    """one UNTRACED reference chain (same seeding discipline as trace_chain); returns its Trajectory"""
+    import contextlib
+    import io
+    ref = load_reference()
+    random.seed(seed)
+    fn = ref.mh.sample_trajectory_single_move if kind == "single" else ref.mh.sample_trajectory
+    saved = ref.mh.tqdm
+    ref.mh.tqdm = lambda rng, **k: rng
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            return fn(n_samples, randomize, sd, sd_graph, init_graph=init_graph, seed=seed)
+    finally:
+        ref.mh.tqdm = saved

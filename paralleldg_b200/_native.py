@@ -22,12 +22,19 @@ EXPORTS = [
     "pdg_set_cliques", "pdg_randomize", "pdg_init_logl", "pdg_run", "pdg_sample", "pdg_sync",
     "pdg_get_counts", "pdg_get_logl", "pdg_compact_updates", "pdg_get_updates", "pdg_enable_move_log",
     "pdg_get_move_log", "pdg_score_sets", "pdg_edge_tallies", "pdg_launch_count",
-    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed", "pdg_host_alloc", "pdg_host_free",
+    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed", "pdg_host_alloc", "pdg_host_free", "pdg_probe",
 ]
 
 
+E_ARG, E_CUDA, E_STATE, E_REPLAY, E_OVERFLOW, E_NUMERIC, E_NOMEM = -1, -2, -3, -4, -5, -6, -7
+
+
 class NativeError(RuntimeError):
-    pass
+    """carries the pdg_error code of include/pdg_b200.h in `.code` (0 when not from the library)"""
+
+    def __init__(self, msg, code=0):
+        RuntimeError.__init__(self, msg)
+        self.code = int(code)
 
 
 class CReplay(C.Structure):
@@ -81,6 +88,7 @@ def lib():
         "pdg_set_seed": (C.c_int, [vp, u64, u32]),
         "pdg_host_alloc": (C.c_int, [C.POINTER(vp), i64]),
         "pdg_host_free": (C.c_int, [vp]),
+        "pdg_probe": (C.c_int, [i32, i32, C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -152,7 +160,7 @@ class Context(object):
                                int(seed) & 0xFFFFFFFFFFFFFFFF, self.n_samples, self.rec_cap)
         if rc != 0:
             self.h = C.c_void_p()
-            raise NativeError("pdg_create failed with code %d (no CUDA device? out of memory?)" % rc)
+            raise NativeError("pdg_create failed with code %d (no CUDA device? out of memory?)" % rc, rc)
         self.mvlog_cap = 0
 
     def close(self):
@@ -169,7 +177,7 @@ class Context(object):
     def _ck(self, rc):
         if rc != 0:
             msg = self.L.pdg_last_error(self.h)
-            raise NativeError("libpdg_b200 error %d: %s" % (rc, msg.decode() if msg else ""))
+            raise NativeError("libpdg_b200 error %d: %s" % (rc, msg.decode() if msg else ""), rc)
 
     def set_seed(self, seed, chain0=0):
         self._ck(self.L.pdg_set_seed(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(chain0)))
@@ -300,3 +308,15 @@ class Context(object):
 
     def launch_count(self):
         return int(self.L.pdg_launch_count(self.h))
+
+
+PROBES = {"fp64_gflops": 0, "l2_read_gbs": 1, "hbm_read_gbs": 2, "red_shared_free_gps": 3, "red_shared_random_gps": 4}
+
+
+def probe(which, device=0):
+    """machine ceilings measured by libpdg_b200.so itself (include/pdg_b200.h: pdg_probe)"""
+    v = C.c_double(0.0)
+    rc = lib().pdg_probe(int(device), PROBES[which], C.byref(v))
+    if rc != 0:
+        raise NativeError("pdg_probe(%s) failed with code %d" % (which, rc), rc)
+    return v.value

@@ -1,14 +1,21 @@
-"""Builds libpdg_b200.so (the CUDA kernels + C-ABI) in-tree with nvcc for sm_100a."""
+"""Builds libpdg_b200.so (the CUDA kernels + C-ABI) in-tree with nvcc for sm_100a.
+
+The C-ABI translation unit and one translation unit per likelihood model (the template
+instantiations of the MH kernel) are compiled in parallel, then linked into one shared library."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libpdg_b200.so")
-SOURCES = ["pdg_b200.cu"]
+SOURCES = ["pdg_b200.cu", "pdg_model_ggm.cu", "pdg_model_loglin.cu", "pdg_model_uniform.cu", "pdg_probe.cu"]
 HEADERS = ["pdg_device.cuh", "pdg_kernels.cuh", "pdg_run.cuh", "pdg_randomize.cuh", "pdg_loglin.cuh",
-           "pdg_tally.cuh", os.path.join("..", "..", "include", "pdg_b200.h")]
+           "pdg_tally.cuh", "pdg_ctx.h", "pdg_model.inl", "pdg_ggm_big.cuh", "pdg_post.cuh",
+           os.path.join("..", "..", "include", "pdg_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _stale():
@@ -22,25 +29,44 @@ def _stale():
     return False
 
 
+def _flags():
+    fl = []
+    for name in ("PDG_LANE_SMEM", "PDG_PHASE_TIMERS"):
+        if os.environ.get(name):
+            fl.append("-D" + name)
+    if os.environ.get("PDG_NO_K4"):
+        fl.append("-DPDG_NO_K4=1")
+    if os.environ.get("PDG_EXTRA_NVCC"):
+        fl += os.environ["PDG_EXTRA_NVCC"].split()
+    return fl
+
+
 def build_native(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if os.environ.get("PDG_LANE_SMEM"):
-        cmd.insert(1, "-DPDG_LANE_SMEM")
-    if os.environ.get("PDG_NO_K4"):
-        cmd.insert(1, "-DPDG_NO_K4=1")
-    if os.environ.get("PDG_PHASE_TIMERS"):
-        cmd.insert(1, "-DPDG_PHASE_TIMERS")
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+    def compile_one(s):
+        o = os.path.join(OBJ, s[:-3] + ".o")
+        cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + _flags()
+        if verbose:
+            cmd.append("-Xptxas=-v")
+        cmd += ["-c", os.path.join(CSRC, s), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (s, r.stdout, r.stderr))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return o
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    subprocess.check_call([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
     return LIB
 
 
 if __name__ == "__main__":
-    build_native(force="--force" in sys.argv, verbose=True)
+    build_native(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

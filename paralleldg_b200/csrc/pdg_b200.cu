@@ -9,173 +9,9 @@
 #include <string>
 #include <vector>
 
-#include "pdg_run.cuh"
+#define PDG_DEFINE_GLOBAL_KERNELS
+#include "pdg_ctx.h"
 #include "pdg_tally.cuh"
-
-// ---------------------------------------------------------------------------------------------
-// logl[0] (mh_parallel.py:59-60 / :217-218): clique scores in tree-node order minus
-// nu_s * score(s) over the DISTINCT non-empty separators (first occurrence in edge order), plus
-// log_prior over cliques and distinct separators (seqdist:44-52).  One warp per chain.
-struct InitSmem { int off_tri, off_lidx, off_idx, off_sc, off_ss, off_cs, off_ssz, off_nu, off_first, total; };
-__host__ __device__ inline InitSmem init_smem_layout(int p, int W, int tri_bytes)
-{
-    InitSmem s; int o = 0;
-    const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
-#ifdef PDG_LANE_SMEM
-    s.off_tri = o; o += PDG_KTRI * 32 * 8;
-    s.off_lidx = o; o += PDG_KT * 32 * 2;
-#else
-    s.off_tri = o; o += tri_bytes;
-    s.off_lidx = o; o += PDG_KT * 32 * 2;
-#endif
-    s.off_sc = o; o += p * 8;
-    s.off_ss = o; o += p * 8;
-    s.off_idx = o; o += a2;
-    s.off_cs = o; o += a2;
-    s.off_ssz = o; o += a2;
-    s.off_nu = o; o += a2;
-    s.off_first = o; o += (p + 15) / 16 * 16;
-    s.total = o;
-    return s;
-}
-
-// one set, same value on every lane: lane 0 carries the key through warp_scores so that logl[0]
-// uses exactly the score function of the sampler
-template <int MODEL, int WMAX>
-__device__ __forceinline__ int set_score_any(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
-                                             const u64 (&X)[WMAX], int lane, double &sc)
-{
-    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
-    double v = 0.0;
-    const int e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, lane == 0, v, wk);
-    sc = __shfl_sync(PDG_FULL, v, 0);
-    return __reduce_or_sync(PDG_FULL, (unsigned)e);
-}
-
-template <int MODEL, int WMAX>
-__global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int p = P.p, W = P.W, lane = threadIdx.x;
-    const long long chain = blockIdx.x;
-    const InitSmem L = init_smem_layout(p, W, tri_bytes_for(P.ll_cap));
-    double *s_sc = (double *)(smem + L.off_sc), *s_ss = (double *)(smem + L.off_ss);
-    unsigned short *s_cs = (unsigned short *)(smem + L.off_cs), *s_ssz = (unsigned short *)(smem + L.off_ssz);
-    unsigned short *s_nu = (unsigned short *)(smem + L.off_nu);
-    unsigned char *s_first = smem + L.off_first;
-    WarpScratch ws;
-    ws.tri32 = (double *)(smem + L.off_tri);
-    ws.idx = (short *)(smem + L.off_idx);
-    ws.kbig = P.kbig;
-    const int slot = (int)chain;
-    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
-    LaneScratch ls;
-    ls.unused = 0;
-    ls.a = (double *)(smem + L.off_tri);
-    ls.idx = (unsigned short *)(smem + L.off_lidx);
-    const u64 *Mc = P.M + (size_t)chain * p * W;
-    const int *E = P.edges + (size_t)chain * 2 * (p - 1);
-    int errflag = 0;
-    for (int t = 0; t < p; ++t) {
-        u64 X[WMAX];
-        load_row<WMAX>(X, Mc + (size_t)t * W, W);
-        int cs = 0;
-#pragma unroll
-        for (int w = 0; w < WMAX; ++w) cs += __popcll(X[w]);
-        double sc = 0.0;
-        if (MODEL != PDG_MODEL_UNIFORM && cs > 0) errflag |= set_score_any<MODEL, WMAX>(P, ws, ls, slot, X, lane, sc);
-        if (lane == 0) { s_sc[t] = sc; s_cs[t] = (unsigned short)cs; }
-    }
-    for (int e = 0; e < p - 1; ++e) {
-        const int a = E[2 * e], b = E[2 * e + 1];
-        u64 X[WMAX];
-        int sz = 0;
-#pragma unroll
-        for (int w = 0; w < WMAX; ++w) { X[w] = (w < W) ? (Mc[(size_t)a * W + w] & Mc[(size_t)b * W + w]) : 0ull; sz += __popcll(X[w]); }
-        int nu = 0; bool first = true;
-        for (int e2 = lane; e2 < p - 1; e2 += 32) {
-            const int a2 = E[2 * e2], b2 = E[2 * e2 + 1];
-            bool same = true;
-#pragma unroll
-            for (int w = 0; w < WMAX; ++w) if (w < W) same = same && ((Mc[(size_t)a2 * W + w] & Mc[(size_t)b2 * W + w]) == X[w]);
-            if (same) { ++nu; if (e2 < e) first = false; }
-        }
-        nu = warp_sum_i(nu);
-        first = __all_sync(PDG_FULL, first);
-        double sc = 0.0;
-        if (MODEL != PDG_MODEL_UNIFORM && first && sz > 0) errflag |= set_score_any<MODEL, WMAX>(P, ws, ls, slot, X, lane, sc);
-        if (lane == 0) { s_ss[e] = sc; s_ssz[e] = (unsigned short)sz; s_nu[e] = (unsigned short)nu; s_first[e] = first ? 1 : 0; }
-    }
-    __syncwarp();
-    if (lane == 0) {
-        double cl = 0.0, lclq = 0.0;
-        for (int t = 0; t < p; ++t) {
-            if (s_cs[t] == 0) continue;
-            cl += s_sc[t];
-            const double a = (double)s_cs[t];
-            if (P.prior == PDG_PRIOR_MBC) lclq += P.prior_a * (a - 1.0);
-            else if (P.prior == PDG_PRIOR_EDGEPENALTY) lclq += -P.prior_a * a * (a - 1.0) / 2.0;
-        }
-        double sc = 0.0, lsep = 0.0;
-        for (int e = 0; e < p - 1; ++e) {
-            if (!s_first[e]) continue;
-            const double b = (double)s_ssz[e];
-            if (P.prior == PDG_PRIOR_MBC) lsep += P.prior_b * b;
-            else if (P.prior == PDG_PRIOR_EDGEPENALTY) lsep += -P.prior_a * b * (b - 1.0) / 2.0;
-            if (s_ssz[e] == 0) continue;
-            sc += (double)s_nu[e] * s_ss[e];
-        }
-        double prior;
-        if (P.prior == PDG_PRIOR_JUMPPENALTY) prior = -P.prior_a * (double)(1 - (kind == PDG_KIND_SINGLE ? 0 : 1));
-        else if (P.prior == PDG_PRIOR_UNIFORM) prior = 0.0;
-        else prior = lclq - lsep;
-        P.logl[(size_t)chain * P.n_samples] = (cl - sc) + prior;
-        P.kcount[chain] = (kind == PDG_KIND_SINGLE) ? 1 : 0;
-        P.nrec[chain] = 0;
-    }
-    if (errflag) atomicOr(&P.err[chain], errflag);
-}
-
-// batch scorer (sd.log_likelihood_partial([c], {})): every LANE takes one complete set, so a
-// warp scores 32 sets per pass through the same routine the sampler uses (warp_scores); sets
-// above PDG_KT vertices and log-linear sets are resolved cooperatively.  grid <= n_chains because
-// the per-warp scratch (large triangles, cell tables) is sized per chain.
-template <int MODEL, int WMAX>
-__global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int W = P.W, lane = threadIdx.x;
-    WarpScratch ws;
-    LaneScratch ls;
-    ws.tri32 = (double *)smem;
-    ls.unused = 0;
-#ifdef PDG_LANE_SMEM
-    ls.a = (double *)smem;
-    ls.idx = (unsigned short *)(smem + PDG_KTRI * 32 * 8);
-    ws.idx = (short *)(smem + PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2);
-#else
-    ls.a = nullptr;
-    ls.idx = (unsigned short *)(smem + tri_bytes_for(P.ll_cap));
-    ws.idx = (short *)(smem + tri_bytes_for(P.ll_cap) + PDG_KT * 32 * 2);
-#endif
-    ws.kbig = P.kbig;
-    const int slot = blockIdx.x;
-    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
-    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
-    for (long long s0 = (long long)blockIdx.x * 32; s0 < n_sets; s0 += (long long)gridDim.x * 32) {
-        const long long s = s0 + lane;
-        u64 X[WMAX];
-        int k = 0;
-#pragma unroll
-        for (int w = 0; w < WMAX; ++w) { X[w] = (s < n_sets && w < W) ? bits[(size_t)s * W + w] : 0ull; k += __popcll(X[w]); }
-        double sc = 0.0;
-        int e = 0;
-        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, s < n_sets && k > 0, sc, wk);
-        if (e) atomicOr(err, e);
-        if (s < n_sets) out[s] = sc;
-        __syncwarp();
-    }
-}
 
 __global__ void k_memo_clear(MemoTable T)
 {
@@ -218,62 +54,9 @@ __global__ void __launch_bounds__(128) k_compact(PdgParams P, const long long *o
 }
 
 // ---------------------------------------------------------------------------------------------
-struct pdg_ctx {
-    int device = 0;
-    PdgParams P;
-    RandScratch Z;
-    cudaStream_t stream = 0;
-    std::string err;
-    bool model_set = false, state_set = false;
-    long long launches = 0;
-    std::vector<void *> owned;
-    // model buffers (replaced on re-set)
-    double *d_A = nullptr, *d_D = nullptr, *d_logD = nullptr, *d_gconst = nullptr;
-    std::vector<void *> model_owned;      // log-linear buffers, freed on re-set / destroy
-    int wmax = 1;                         // compile-time word count the kernels are dispatched on
-    int wpc = 8;                          // warps (= chains) per CTA of the MH kernel (8 -> one CTA per SM at 1024 chains)
-    bool smem_state = false;
-    bool light = false;                   // log-linear model with few rows: the 128-register MH kernel
-    int memo_bits = 24;
-    // compaction
-    long long *d_offsets = nullptr;
-    pdg_update *d_packed = nullptr;
-    u64 *d_packed_bits = nullptr;
-    long long packed_total = -1, packed_cap = 0;
-    int *d_since = nullptr;               // edge-tally scratch, kept between calls
-    unsigned long long *d_tally = nullptr;
-    // replay staging
-    std::vector<void *> replay_tmp;
-    // CUDA-event timing of the MH and randomisation launches
-    bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_run, ev_rand;
-};
-
-static void time_begin(pdg_ctx *ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &v)
-{
-    if (!ctx->timing) return;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, ctx->stream);
-    v.push_back(std::make_pair(a, b));
-}
-static void time_end(pdg_ctx *ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &v)
-{
-    if (!ctx->timing) return;
-    cudaEventRecord(v.back().second, ctx->stream);
-}
-
-static int fail(pdg_ctx *c, int code, const std::string &msg)
-{
-    if (c) c->err = msg;
-    return code;
-}
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(ctx, PDG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
+#define fail pdg_fail
+#define time_begin pdg_time_begin
+#define time_end pdg_time_end
 
 template <typename T>
 static cudaError_t dalloc(pdg_ctx *ctx, T **ptr, size_t count)
@@ -284,123 +67,13 @@ static cudaError_t dalloc(pdg_ctx *ctx, T **ptr, size_t count)
     return e;
 }
 
-template <typename F>
-static int set_smem(pdg_ctx *ctx, F f, int bytes)
-{
-    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    return PDG_OK;
-}
-
-template <int MODEL, int WMAX, bool SS, bool LIGHT>
-static int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
-{
-    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
-    const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
-    const int per_warp = (randomize > 0 && LR.total > L.total) ? LR.total : L.total;
-    const int wpc = ctx->wpc, sm = per_warp * wpc;
-    int rc;
-    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT>, sm))) return rc;
-    const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
-    time_begin(ctx, ctx->ev_run);
-    // chains of one CTA re-align every `lockstep` iterations (power of two, 0 = never)
-    int lockstep = 0;
-    // (not for log-linear models with many rows: a table scan then costs ~100x an iteration and the
-    // other chains of the CTA must not wait for it)
-    if (wpc > 1 && !(MODEL == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192)) {
-        lockstep = 16;
-        if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
-        if (lockstep & (lockstep - 1)) lockstep = 0;
-    }
-    k_mh_run<MODEL, WMAX, SS, LIGHT><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
-    time_end(ctx, ctx->ev_run);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return PDG_OK;
-}
-
-template <int MODEL, int WMAX, bool SS>
-static int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
-{
-    if constexpr (MODEL == PDG_MODEL_LOGLIN) {
-        if (ctx->light) return launch_run_k<MODEL, WMAX, SS, true>(ctx, kind, b, e, R, randomize);
-    }
-    return launch_run_k<MODEL, WMAX, SS, false>(ctx, kind, b, e, R, randomize);
-}
-
-template <int MODEL, int WMAX>
-static int launch_run_w(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long rz)
-{
-    if (ctx->smem_state) return launch_run_t<MODEL, WMAX, true>(ctx, kind, b, e, R, rz);
-    return launch_run_t<MODEL, WMAX, false>(ctx, kind, b, e, R, rz);
-}
-
-template <int MODEL>
-static int launch_run_m(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long rz)
-{
-    switch (ctx->wmax) {
-    case 1: return launch_run_w<MODEL, 1>(ctx, kind, b, e, R, rz);
-    case 2: return launch_run_w<MODEL, 2>(ctx, kind, b, e, R, rz);
-    case 4: return launch_run_w<MODEL, 4>(ctx, kind, b, e, R, rz);
-    default: return launch_run_w<MODEL, 8>(ctx, kind, b, e, R, rz);
-    }
-}
-
 // randomize > 0: the kernel randomises every chain's junction tree at every multiple of it
 static int run_dispatch(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize = 0)
 {
     switch (ctx->P.model) {
-    case PDG_MODEL_GGM: return launch_run_m<PDG_MODEL_GGM>(ctx, kind, b, e, R, randomize);
-    case PDG_MODEL_LOGLIN: return launch_run_m<PDG_MODEL_LOGLIN>(ctx, kind, b, e, R, randomize);
-    default: return launch_run_m<PDG_MODEL_UNIFORM>(ctx, kind, b, e, R, randomize);
-    }
-}
-
-template <int MODEL, int WMAX>
-static int launch_init_t(pdg_ctx *ctx, int kind)
-{
-    const InitSmem L = init_smem_layout(ctx->P.p, ctx->P.W, tri_bytes_for(ctx->P.ll_cap));
-    int rc;
-    if ((rc = set_smem(ctx, k_init_logl<MODEL, WMAX>, L.total))) return rc;
-    k_init_logl<MODEL, WMAX><<<(unsigned)ctx->P.n_chains, 32, L.total, ctx->stream>>>(ctx->P, kind);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return PDG_OK;
-}
-
-template <int MODEL>
-static int launch_init_m(pdg_ctx *ctx, int kind)
-{
-    switch (ctx->wmax) {
-    case 1: return launch_init_t<MODEL, 1>(ctx, kind);
-    case 2: return launch_init_t<MODEL, 2>(ctx, kind);
-    case 4: return launch_init_t<MODEL, 4>(ctx, kind);
-    default: return launch_init_t<MODEL, 8>(ctx, kind);
-    }
-}
-
-template <int MODEL, int WMAX>
-static int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
-{
-    long long grid = n_sets < ctx->P.n_chains ? n_sets : ctx->P.n_chains;
-#ifdef PDG_LANE_SMEM
-    const int sm = PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
-#else
-    const int sm = tri_bytes_for(ctx->P.ll_cap) + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
-#endif
-    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return PDG_OK;
-}
-
-template <int MODEL>
-static int launch_score_m(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
-{
-    switch (ctx->wmax) {
-    case 1: return launch_score_t<MODEL, 1>(ctx, d_bits, n_sets, d_out, d_err);
-    case 2: return launch_score_t<MODEL, 2>(ctx, d_bits, n_sets, d_out, d_err);
-    case 4: return launch_score_t<MODEL, 4>(ctx, d_bits, n_sets, d_out, d_err);
-    default: return launch_score_t<MODEL, 8>(ctx, d_bits, n_sets, d_out, d_err);
+    case PDG_MODEL_GGM: return pdg_launch_run_ggm(ctx, kind, b, e, R, randomize);
+    case PDG_MODEL_LOGLIN: return pdg_launch_run_loglin(ctx, kind, b, e, R, randomize);
+    default: return pdg_launch_run_uniform(ctx, kind, b, e, R, randomize);
     }
 }
 
@@ -441,7 +114,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
 {
     if (!out) return PDG_E_ARG;
     *out = nullptr;
-    if (p < 2 || p > 64 * PDG_WMAX_LIMIT || n_chains < 1 || n_samples < 1 || rec_cap < 0) return PDG_E_ARG;
+    if (p < 2 || p > 64 * PDG_WMAX_LIMIT || n_chains < 1 || n_samples < 1 || n_samples > 2147483647LL || rec_cap < 0) return PDG_E_ARG;   // pdg_update.i is 32 bits wide
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PDG_E_CUDA;   // no CPU fallback
     if (device < 0 || device >= ndev) return PDG_E_ARG;
@@ -493,6 +166,14 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
         ctx->smem_state = (size_t)p * W * 16 <= 8192;
         MemoTable &T = P.memo;
         T.W = (ctx->wmax == 1) ? 1 : W;
+        // the table never takes more than half of the memory that is still free on the device
+        {
+            size_t mfree = 0, mtotal = 0;
+            if (e == cudaSuccess && cudaMemGetInfo(&mfree, &mtotal) == cudaSuccess) {
+                const size_t per_slot = (ctx->wmax == 1) ? 16 : (size_t)16 + 8 * (size_t)W;
+                while (ctx->memo_bits > 8 && (per_slot << ctx->memo_bits) > mfree / 2) --ctx->memo_bits;
+            }
+        }
         T.mask = (1u << ctx->memo_bits) - 1u;
         const size_t slots = (size_t)1 << ctx->memo_bits;
         T.kv = nullptr; T.tag = nullptr; T.keyw = nullptr; T.val = nullptr;
@@ -507,6 +188,13 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
         for (void *v : ctx->owned) cudaFree(v);
         delete ctx;
         return e == cudaErrorMemoryAllocation ? PDG_E_NOMEM : PDG_E_CUDA;
+    }
+    // the memo table must never be read as allocated: cudaMalloc hands back the previous owner's
+    // bytes (possibly another model's {clique -> score} entries)
+    if (memo_clear(ctx) != PDG_OK || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        for (void *v : ctx->owned) cudaFree(v);
+        delete ctx;
+        return PDG_E_CUDA;
     }
     *out = ctx;
     return PDG_OK;
@@ -527,6 +215,11 @@ int pdg_destroy(pdg_ctx *ctx)
     if (ctx->d_since) { cudaFree(ctx->d_since); cudaFree(ctx->d_tally); }
     if (ctx->d_packed) cudaFree(ctx->d_packed);
     if (ctx->d_packed_bits) cudaFree(ctx->d_packed_bits);
+    if (ctx->d_sbits) { cudaFree(ctx->d_sbits); cudaFree(ctx->d_sout); }
+    if (ctx->d_serr) cudaFree(ctx->d_serr);
+    for (auto *v : {&ctx->ev_run, &ctx->ev_rand, &ctx->ev_free})
+        for (auto &e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->P.ml_dlik) { cudaFree(ctx->P.ml_dlik); cudaFree(ctx->P.ml_dprior); cudaFree(ctx->P.ml_logq); cudaFree(ctx->P.ml_u); cudaFree(ctx->P.ml_acc); cudaFree(ctx->P.ml_U); }
     delete ctx;
     return PDG_OK;
@@ -567,7 +260,7 @@ int pdg_set_model_uniform(pdg_ctx *ctx)
     if (!ctx) return PDG_E_ARG;
     ctx->P.model = PDG_MODEL_UNIFORM; ctx->P.ll_cap = 0;
     ctx->model_set = true;
-    return PDG_OK;
+    return memo_clear(ctx);                 // cached scores belong to the model that produced them
 }
 
 int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, double delta, const void *gconst)
@@ -604,7 +297,7 @@ int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, dou
     P.delta = delta; P.nobs = (double)n;
     P.model = PDG_MODEL_GGM; P.ll_cap = 0;
     ctx->model_set = true;
-    return PDG_OK;
+    return memo_clear(ctx);                 // cached scores belong to the model that produced them
 }
 
 int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int64_t nrows, double cell_alpha,
@@ -614,56 +307,71 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     if (n_ktab > 0 && (!ktab || !alphatab || !lgtab)) return PDG_E_ARG;
     CK(cudaSetDevice(ctx->device));
     PdgParams &P = ctx->P;
-    for (void *v : ctx->model_owned) cudaFree(v);
-    ctx->model_owned.clear();
-    auto own = [&](size_t bytes, void **out) -> cudaError_t {
-        cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
-        if (e == cudaSuccess) ctx->model_owned.push_back(*out);
-        return e;
-    };
-    void *d_data = nullptr, *d_lv = nullptr, *d_k = nullptr, *d_a = nullptr, *d_lg = nullptr;
-    // columns padded to a 16-byte stride, an all-zero column behind the last one and 4 KB of slack:
-    // the dense scan (pdg_loglin.cuh) then needs no load predicates
-    const size_t ld = ((size_t)nrows + 15) & ~(size_t)15;
-    CK(own((size_t)(P.p + 1) * ld + 4096, &d_data));
-    CK(own((size_t)P.p * sizeof(int), &d_lv));
-    CK(cudaMemsetAsync(d_data, 0, (size_t)(P.p + 1) * ld + 4096, ctx->stream));
-    CK(cudaMemcpy2DAsync(d_data, ld, data, (size_t)nrows, (size_t)nrows, (size_t)P.p, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(d_lv, levels, (size_t)P.p * sizeof(int), cudaMemcpyDefault, ctx->stream));
-    if (n_ktab > 0) {
-        CK(own((size_t)n_ktab * 8, &d_k));
-        CK(own((size_t)n_ktab * 8, &d_a));
-        CK(own((size_t)n_ktab * (size_t)(nrows + 2) * 8, &d_lg));
-        CK(cudaMemcpyAsync(d_k, ktab, (size_t)n_ktab * 8, cudaMemcpyDefault, ctx->stream));
-        CK(cudaMemcpyAsync(d_a, alphatab, (size_t)n_ktab * 8, cudaMemcpyDefault, ctx->stream));
-        CK(cudaMemcpyAsync(d_lg, lgtab, (size_t)n_ktab * (size_t)(nrows + 2) * 8, cudaMemcpyDefault, ctx->stream));
-    }
     // dense cell counters: one table per warp slot (= chain); larger sets go through a pool of
     // hashed tables
     int hist_cells = 1 << 16;
     if (const char *v = getenv("PDG_HIST_CELLS")) { const int x = atoi(v); if (x >= 2 && x <= (1 << 16)) hist_cells = x; }
-    void *d_hist = nullptr;
-    CK(own((size_t)P.n_chains * hist_cells * 4, &d_hist));
-    CK(cudaMemsetAsync(d_hist, 0, (size_t)P.n_chains * hist_cells * 4, ctx->stream));
+    // columns padded to a 16-byte stride, an all-zero column behind the last one and 4 KB of slack:
+    // the dense scan (pdg_loglin.cuh) then needs no load predicates
+    const size_t ld = ((size_t)nrows + 15) & ~(size_t)15;
+    const size_t data_bytes = (size_t)(P.p + 1) * ld + 4096;
     LoglinSparse sp;
     sp.nsp = (int)(P.n_chains < 64 ? P.n_chains : 64);
     int hs = 1;
     while (hs < 2 * nrows) hs <<= 1;
     sp.hslots = hs;
-    void *d_lock = nullptr, *d_hk = nullptr, *d_hc = nullptr, *d_cc = nullptr;
-    CK(own((size_t)sp.nsp * 4, &d_lock));
-    CK(own((size_t)sp.nsp * hs * 8, &d_hk));
-    CK(own((size_t)sp.nsp * hs * 4, &d_hc));
-    CK(own((size_t)sp.nsp * (size_t)(nrows + 2) * 4, &d_cc));
-    CK(cudaMemsetAsync(d_lock, 0, (size_t)sp.nsp * 4, ctx->stream));
-    CK(cudaMemsetAsync(d_hk, 0, (size_t)sp.nsp * hs * 8, ctx->stream));
-    CK(cudaMemsetAsync(d_hc, 0, (size_t)sp.nsp * hs * 4, ctx->stream));
-    CK(cudaMemsetAsync(d_cc, 0, (size_t)sp.nsp * (size_t)(nrows + 2) * 4, ctx->stream));
-    sp.lock = (int *)d_lock; sp.hkeys = (u64 *)d_hk; sp.hcnt = (unsigned int *)d_hc; sp.cc = (unsigned int *)d_cc;
-    CK(cudaStreamSynchronize(ctx->stream));
-    P.data = (const unsigned char *)d_data; P.data_ld = (long long)ld; P.levels = (const int *)d_lv; P.nrows = nrows; P.cell_alpha = cell_alpha;
-    P.n_ktab = n_ktab; P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
-    P.hist = (unsigned int *)d_hist; P.hist_cells = hist_cells; P.sp = sp;
+    // A pooled context that is re-armed with a model of the same shape keeps its buffers: the count
+    // tables (0.5 GB at 1024 chains) are left all-zero by every scan, so only the data and the
+    // lgamma tables are uploaded again -- no free / malloc / memset per call.
+    const long long shape[4] = {(long long)nrows, (long long)n_ktab, (long long)hist_cells, P.n_chains};
+    const bool reuse = !ctx->model_owned.empty() && ctx->P.model == PDG_MODEL_LOGLIN &&
+                       shape[0] == ctx->ll_shape[0] && shape[1] == ctx->ll_shape[1] &&
+                       shape[2] == ctx->ll_shape[2] && shape[3] == ctx->ll_shape[3];
+    if (!reuse) {
+        for (void *v : ctx->model_owned) cudaFree(v);
+        ctx->model_owned.clear();
+        ctx->ll_shape[0] = -1;
+        auto own = [&](size_t bytes, void **out) -> cudaError_t {
+            cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+            if (e == cudaSuccess) ctx->model_owned.push_back(*out);
+            return e;
+        };
+        void *d_data = nullptr, *d_lv = nullptr, *d_k = nullptr, *d_a = nullptr, *d_lg = nullptr;
+        void *d_hist = nullptr, *d_lock = nullptr, *d_hk = nullptr, *d_hc = nullptr, *d_cc = nullptr;
+        CK(own(data_bytes, &d_data));
+        CK(own((size_t)P.p * sizeof(int), &d_lv));
+        CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * 8, &d_k));
+        CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * 8, &d_a));
+        CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * (size_t)(nrows + 2) * 8, &d_lg));
+        CK(own((size_t)P.n_chains * hist_cells * 4, &d_hist));
+        CK(own((size_t)sp.nsp * 4, &d_lock));
+        CK(own((size_t)sp.nsp * hs * 8, &d_hk));
+        CK(own((size_t)sp.nsp * hs * 4, &d_hc));
+        CK(own((size_t)sp.nsp * (size_t)(nrows + 2) * 4, &d_cc));
+        CK(cudaMemsetAsync(d_data, 0, data_bytes, ctx->stream));
+        CK(cudaMemsetAsync(d_hist, 0, (size_t)P.n_chains * hist_cells * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_lock, 0, (size_t)sp.nsp * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_hk, 0, (size_t)sp.nsp * hs * 8, ctx->stream));
+        CK(cudaMemsetAsync(d_hc, 0, (size_t)sp.nsp * hs * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_cc, 0, (size_t)sp.nsp * (size_t)(nrows + 2) * 4, ctx->stream));
+        P.data = (const unsigned char *)d_data; P.levels = (const int *)d_lv;
+        P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
+        P.hist = (unsigned int *)d_hist;
+        sp.lock = (int *)d_lock; sp.hkeys = (u64 *)d_hk; sp.hcnt = (unsigned int *)d_hc; sp.cc = (unsigned int *)d_cc;
+        P.sp = sp;
+        for (int q = 0; q < 4; ++q) ctx->ll_shape[q] = shape[q];
+    }
+    // (padding rows / the zero column were cleared when the buffer was created and are never written)
+    CK(cudaMemcpy2DAsync((void *)P.data, ld, data, (size_t)nrows, (size_t)nrows, (size_t)P.p, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync((void *)P.levels, levels, (size_t)P.p * sizeof(int), cudaMemcpyDefault, ctx->stream));
+    if (n_ktab > 0) {
+        CK(cudaMemcpyAsync((void *)P.ktab, ktab, (size_t)n_ktab * 8, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync((void *)P.alphatab, alphatab, (size_t)n_ktab * 8, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync((void *)P.lgtab, lgtab, (size_t)n_ktab * (size_t)(nrows + 2) * 8, cudaMemcpyDefault, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));       // the host arrays may go away after the call
+    P.data_ld = (long long)ld; P.nrows = nrows; P.cell_alpha = cell_alpha;
+    P.n_ktab = n_ktab; P.hist_cells = hist_cells;
     P.model = PDG_MODEL_LOGLIN;
     // few rows: a scan is cheap, so the light kernel (two CTAs per SM, 1024-cell tables) runs the chains
     ctx->light = nrows <= 8192;
@@ -679,7 +387,7 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
         P.ll_cap >>= 1;
     }
     ctx->model_set = true;
-    return PDG_OK;
+    return memo_clear(ctx);                 // cached scores belong to the model that produced them
 }
 
 static int launch_derived(pdg_ctx *ctx, long long b, long long n)
@@ -769,9 +477,9 @@ int pdg_init_logl(pdg_ctx *ctx, int kind)
     // a run starts with an empty memo: nothing scored in an earlier run is reused
     if ((rc = memo_clear(ctx))) return rc;
     switch (ctx->P.model) {
-    case PDG_MODEL_GGM: rc = launch_init_m<PDG_MODEL_GGM>(ctx, kind); break;
-    case PDG_MODEL_LOGLIN: rc = launch_init_m<PDG_MODEL_LOGLIN>(ctx, kind); break;
-    default: rc = launch_init_m<PDG_MODEL_UNIFORM>(ctx, kind); break;
+    case PDG_MODEL_GGM: rc = pdg_launch_init_ggm(ctx, kind); break;
+    case PDG_MODEL_LOGLIN: rc = pdg_launch_init_loglin(ctx, kind); break;
+    default: rc = pdg_launch_init_uniform(ctx, kind); break;
     }
     if (rc) return rc;
     k_snapshot_graph<<<(unsigned)ctx->P.n_chains, 32, 0, ctx->stream>>>(ctx->P);
@@ -969,24 +677,27 @@ int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores)
     if (n_sets == 0) return PDG_OK;
     CK(cudaSetDevice(ctx->device));
     PdgParams &P = ctx->P;
-    u64 *d_bits = nullptr; double *d_out = nullptr; int *d_err = nullptr;
-    CK(cudaMalloc((void **)&d_bits, (size_t)n_sets * P.W * 8));
-    CK(cudaMalloc((void **)&d_out, (size_t)n_sets * 8));
-    CK(cudaMalloc((void **)&d_err, 4));
-    CK(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
-    CK(cudaMemcpyAsync(d_bits, bits, (size_t)n_sets * P.W * 8, cudaMemcpyDefault, ctx->stream));
+    if (n_sets > ctx->score_cap) {           // staging kept by the context, freed by pdg_destroy
+        if (ctx->d_sbits) { cudaFree(ctx->d_sbits); cudaFree(ctx->d_sout); ctx->d_sbits = nullptr; ctx->d_sout = nullptr; }
+        ctx->score_cap = 0;
+        CK(cudaMalloc((void **)&ctx->d_sbits, (size_t)n_sets * P.W * 8));
+        CK(cudaMalloc((void **)&ctx->d_sout, (size_t)n_sets * 8));
+        ctx->score_cap = n_sets;
+    }
+    if (!ctx->d_serr) CK(cudaMalloc((void **)&ctx->d_serr, 4));
+    CK(cudaMemsetAsync(ctx->d_serr, 0, 4, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sbits, bits, (size_t)n_sets * P.W * 8, cudaMemcpyDefault, ctx->stream));
     int rc;
     switch (P.model) {
-    case PDG_MODEL_GGM: rc = launch_score_m<PDG_MODEL_GGM>(ctx, d_bits, n_sets, d_out, d_err); break;
-    case PDG_MODEL_LOGLIN: rc = launch_score_m<PDG_MODEL_LOGLIN>(ctx, d_bits, n_sets, d_out, d_err); break;
-    default: rc = launch_score_m<PDG_MODEL_UNIFORM>(ctx, d_bits, n_sets, d_out, d_err); break;
+    case PDG_MODEL_GGM: rc = pdg_launch_score_ggm(ctx, ctx->d_sbits, n_sets, ctx->d_sout, ctx->d_serr); break;
+    case PDG_MODEL_LOGLIN: rc = pdg_launch_score_loglin(ctx, ctx->d_sbits, n_sets, ctx->d_sout, ctx->d_serr); break;
+    default: rc = pdg_launch_score_uniform(ctx, ctx->d_sbits, n_sets, ctx->d_sout, ctx->d_serr); break;
     }
     if (rc) return rc;
     int herr = 0;
-    CK(cudaMemcpyAsync(scores, d_out, (size_t)n_sets * 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(scores, ctx->d_sout, (size_t)n_sets * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(&herr, ctx->d_serr, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_bits); cudaFree(d_out); cudaFree(d_err);
     if (herr) return fail(ctx, PDG_E_NUMERIC, "scorer: non-SPD pivot or clique above the supported size");
     return PDG_OK;
 }
@@ -1034,8 +745,9 @@ int pdg_enable_timing(pdg_ctx *ctx, int on)
 {
     if (!ctx) return PDG_E_ARG;
     ctx->timing = on != 0;
-    for (auto &e : ctx->ev_run) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (auto &e : ctx->ev_rand) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    // the recorded pairs go back to the pool (destroyed with the context)
+    for (auto &e : ctx->ev_run) ctx->ev_free.push_back(e);
+    for (auto &e : ctx->ev_rand) ctx->ev_free.push_back(e);
     ctx->ev_run.clear(); ctx->ev_rand.clear();
     return PDG_OK;
 }
@@ -1064,12 +776,6 @@ int pdg_get_work(pdg_ctx *ctx, int64_t work[16])
     CK(cudaMemcpy(h.data(), ctx->P.work, h.size() * 8, cudaMemcpyDeviceToHost));
     for (int q = 0; q < 16; ++q) work[q] = 0;
     for (size_t c = 0; c < (size_t)ctx->P.n_chains; ++c) for (int q = 0; q < 16; ++q) work[q] += (int64_t)h[c * 16 + q];
-#ifdef PDG_PHASE_TIMERS
-    { unsigned long long g[8]; cudaMemcpyFromSymbol(g, g_pt, sizeof(g));
-      fprintf(stderr, "lane scorer cycles: idx %llu gather %llu ldl %llu log %llu score %llu | calls K4 %llu K8 %llu\n", g[0], g[1], g[2], g[3], g[4], g[5], g[6]);
-      unsigned long long kh[2][32]; cudaMemcpyFromSymbol(kh, g_kh, sizeof(kh));
-      for (int k = 0; k < 32; ++k) if (kh[0][k]) fprintf(stderr, "  scans k=%d: %llu, %.0f cycles each\n", k, kh[0][k], (double)kh[1][k] / (double)kh[0][k]); }
-#endif
     return PDG_OK;
 }
 

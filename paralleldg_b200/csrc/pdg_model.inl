@@ -1,0 +1,307 @@
+// Kernels and launchers that are instantiated per likelihood model.  Included by exactly one
+// translation unit per model (pdg_model_<name>.cu defines PDG_TU_MODEL and PDG_TU_NAME), so that
+// the three sets of template instantiations compile in parallel.
+#include <stdlib.h>
+
+#include "pdg_ctx.h"
+#include "pdg_run.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// logl[0] (mh_parallel.py:59-60 / :217-218): clique scores in tree-node order minus
+// nu_s * score(s) over the DISTINCT non-empty separators (first occurrence in edge order), plus
+// log_prior over cliques and distinct separators (seqdist:44-52).  One warp per chain.
+struct InitSmem { int off_tri, off_lidx, off_idx, off_sc, off_ss, off_cs, off_ssz, off_nu, off_first, total; };
+__host__ __device__ inline InitSmem init_smem_layout(int p, int W, int tri_bytes)
+{
+    InitSmem s; int o = 0;
+    const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
+#ifdef PDG_LANE_SMEM
+    s.off_tri = o; o += PDG_KTRI * 32 * 8;
+    s.off_lidx = o; o += PDG_KT * 32 * 2;
+#else
+    s.off_tri = o; o += tri_bytes;
+    s.off_lidx = o; o += PDG_KT * 32 * 2;
+#endif
+    s.off_sc = o; o += p * 8;
+    s.off_ss = o; o += p * 8;
+    s.off_idx = o; o += a2;
+    s.off_cs = o; o += a2;
+    s.off_ssz = o; o += a2;
+    s.off_nu = o; o += a2;
+    s.off_first = o; o += (p + 15) / 16 * 16;
+    s.total = o;
+    return s;
+}
+
+// one set, same value on every lane: lane 0 carries the key through warp_scores so that logl[0]
+// uses exactly the score function of the sampler
+template <int MODEL, int WMAX>
+__device__ __forceinline__ int set_score_any(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
+                                             const u64 (&X)[WMAX], int lane, double &sc)
+{
+    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    double v = 0.0;
+    const int e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, lane == 0, v, wk);
+    sc = __shfl_sync(PDG_FULL, v, 0);
+    return __reduce_or_sync(PDG_FULL, (unsigned)e);
+}
+
+template <int MODEL, int WMAX>
+__global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int p = P.p, W = P.W, lane = threadIdx.x;
+    const long long chain = blockIdx.x;
+    const InitSmem L = init_smem_layout(p, W, tri_bytes_for(P.ll_cap));
+    double *s_sc = (double *)(smem + L.off_sc), *s_ss = (double *)(smem + L.off_ss);
+    unsigned short *s_cs = (unsigned short *)(smem + L.off_cs), *s_ssz = (unsigned short *)(smem + L.off_ssz);
+    unsigned short *s_nu = (unsigned short *)(smem + L.off_nu);
+    unsigned char *s_first = smem + L.off_first;
+    WarpScratch ws;
+    ws.tri32 = (double *)(smem + L.off_tri);
+    ws.idx = (short *)(smem + L.off_idx);
+    ws.kbig = P.kbig;
+    const int slot = (int)chain;
+    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    LaneScratch ls;
+    ls.unused = 0;
+    ls.a = (double *)(smem + L.off_tri);
+    ls.idx = (unsigned short *)(smem + L.off_lidx);
+    const u64 *Mc = P.M + (size_t)chain * p * W;
+    const int *E = P.edges + (size_t)chain * 2 * (p - 1);
+    int errflag = 0;
+    for (int t = 0; t < p; ++t) {
+        u64 X[WMAX];
+        load_row<WMAX>(X, Mc + (size_t)t * W, W);
+        int cs = 0;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) cs += __popcll(X[w]);
+        double sc = 0.0;
+        if (MODEL != PDG_MODEL_UNIFORM && cs > 0) errflag |= set_score_any<MODEL, WMAX>(P, ws, ls, slot, X, lane, sc);
+        if (lane == 0) { s_sc[t] = sc; s_cs[t] = (unsigned short)cs; }
+    }
+    for (int e = 0; e < p - 1; ++e) {
+        const int a = E[2 * e], b = E[2 * e + 1];
+        u64 X[WMAX];
+        int sz = 0;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) { X[w] = (w < W) ? (Mc[(size_t)a * W + w] & Mc[(size_t)b * W + w]) : 0ull; sz += __popcll(X[w]); }
+        int nu = 0; bool first = true;
+        for (int e2 = lane; e2 < p - 1; e2 += 32) {
+            const int a2 = E[2 * e2], b2 = E[2 * e2 + 1];
+            bool same = true;
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w) if (w < W) same = same && ((Mc[(size_t)a2 * W + w] & Mc[(size_t)b2 * W + w]) == X[w]);
+            if (same) { ++nu; if (e2 < e) first = false; }
+        }
+        nu = warp_sum_i(nu);
+        first = __all_sync(PDG_FULL, first);
+        double sc = 0.0;
+        if (MODEL != PDG_MODEL_UNIFORM && first && sz > 0) errflag |= set_score_any<MODEL, WMAX>(P, ws, ls, slot, X, lane, sc);
+        if (lane == 0) { s_ss[e] = sc; s_ssz[e] = (unsigned short)sz; s_nu[e] = (unsigned short)nu; s_first[e] = first ? 1 : 0; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double cl = 0.0, lclq = 0.0;
+        for (int t = 0; t < p; ++t) {
+            if (s_cs[t] == 0) continue;
+            cl += s_sc[t];
+            const double a = (double)s_cs[t];
+            if (P.prior == PDG_PRIOR_MBC) lclq += P.prior_a * (a - 1.0);
+            else if (P.prior == PDG_PRIOR_EDGEPENALTY) lclq += -P.prior_a * a * (a - 1.0) / 2.0;
+        }
+        double sc = 0.0, lsep = 0.0;
+        for (int e = 0; e < p - 1; ++e) {
+            if (!s_first[e]) continue;
+            const double b = (double)s_ssz[e];
+            if (P.prior == PDG_PRIOR_MBC) lsep += P.prior_b * b;
+            else if (P.prior == PDG_PRIOR_EDGEPENALTY) lsep += -P.prior_a * b * (b - 1.0) / 2.0;
+            if (s_ssz[e] == 0) continue;
+            sc += (double)s_nu[e] * s_ss[e];
+        }
+        double prior;
+        if (P.prior == PDG_PRIOR_JUMPPENALTY) prior = -P.prior_a * (double)(1 - (kind == PDG_KIND_SINGLE ? 0 : 1));
+        else if (P.prior == PDG_PRIOR_UNIFORM) prior = 0.0;
+        else prior = lclq - lsep;
+        P.logl[(size_t)chain * P.n_samples] = (cl - sc) + prior;
+        P.kcount[chain] = (kind == PDG_KIND_SINGLE) ? 1 : 0;
+        P.nrec[chain] = 0;
+    }
+    if (errflag) atomicOr(&P.err[chain], errflag);
+}
+
+// batch scorer (sd.log_likelihood_partial([c], {})): every LANE takes one complete set, so a
+// warp scores 32 sets per pass through the same routine the sampler uses (warp_scores); sets
+// above PDG_KT vertices and log-linear sets are resolved cooperatively.  grid <= n_chains because
+// the per-warp scratch (large triangles, cell tables) is sized per chain.
+template <int MODEL, int WMAX>
+__global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int W = P.W, lane = threadIdx.x;
+    WarpScratch ws;
+    LaneScratch ls;
+    ws.tri32 = (double *)smem;
+    ls.unused = 0;
+#ifdef PDG_LANE_SMEM
+    ls.a = (double *)smem;
+    ls.idx = (unsigned short *)(smem + PDG_KTRI * 32 * 8);
+    ws.idx = (short *)(smem + PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2);
+#else
+    ls.a = nullptr;
+    ls.idx = (unsigned short *)(smem + tri_bytes_for(P.ll_cap));
+    ws.idx = (short *)(smem + tri_bytes_for(P.ll_cap) + PDG_KT * 32 * 2);
+#endif
+    ws.kbig = P.kbig;
+    const int slot = blockIdx.x;
+    ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
+    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    for (long long s0 = (long long)blockIdx.x * 32; s0 < n_sets; s0 += (long long)gridDim.x * 32) {
+        const long long s = s0 + lane;
+        u64 X[WMAX];
+        int k = 0;
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) { X[w] = (s < n_sets && w < W) ? bits[(size_t)s * W + w] : 0ull; k += __popcll(X[w]); }
+        double sc = 0.0;
+        int e = 0;
+        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, s < n_sets && k > 0, sc, wk);
+        if (e) atomicOr(err, e);
+        if (s < n_sets) out[s] = sc;
+        __syncwarp();
+    }
+}
+
+template <typename F>
+int set_smem(pdg_ctx *ctx, F f, int bytes)
+{
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return PDG_OK;
+}
+
+template <int MODEL, int WMAX, bool SS, bool LIGHT>
+int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
+{
+    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
+    const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
+    const int per_warp = (randomize > 0 && LR.total > L.total) ? LR.total : L.total;
+    const int wpc = ctx->wpc, sm = per_warp * wpc;
+    int rc;
+    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT>, sm))) return rc;
+    const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
+    pdg_time_begin(ctx, ctx->ev_run);
+    // chains of one CTA re-align every `lockstep` iterations (power of two, 0 = never)
+    int lockstep = 0;
+    // (not for log-linear models with many rows: a table scan then costs ~100x an iteration and the
+    // other chains of the CTA must not wait for it)
+    if (wpc > 1 && !(MODEL == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192)) {
+        lockstep = 16;
+        if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
+        if (lockstep & (lockstep - 1)) lockstep = 0;
+    }
+    k_mh_run<MODEL, WMAX, SS, LIGHT><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
+    pdg_time_end(ctx, ctx->ev_run);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PDG_OK;
+}
+
+template <int MODEL, int WMAX, bool SS>
+int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
+{
+    if constexpr (MODEL == PDG_MODEL_LOGLIN) {
+        if (ctx->light) return launch_run_k<MODEL, WMAX, SS, true>(ctx, kind, b, e, R, randomize);
+    }
+    return launch_run_k<MODEL, WMAX, SS, false>(ctx, kind, b, e, R, randomize);
+}
+
+// The chain state lives in shared memory whenever p * W * 16 <= 8192 bytes (pdg_create): always for
+// one- and two-word bitsets (p <= 128), never for more than four words (p >= 257), so only the
+// four-word kernels exist in both forms.
+template <int MODEL, int WMAX>
+int launch_run_w(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long rz)
+{
+    if constexpr (WMAX <= 2) return launch_run_t<MODEL, WMAX, true>(ctx, kind, b, e, R, rz);
+    else if constexpr (WMAX == 8) return launch_run_t<MODEL, WMAX, false>(ctx, kind, b, e, R, rz);
+    else {
+        if (ctx->smem_state) return launch_run_t<MODEL, WMAX, true>(ctx, kind, b, e, R, rz);
+        return launch_run_t<MODEL, WMAX, false>(ctx, kind, b, e, R, rz);
+    }
+}
+
+template <int MODEL>
+int launch_run_m(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long rz)
+{
+    switch (ctx->wmax) {
+    case 1: return launch_run_w<MODEL, 1>(ctx, kind, b, e, R, rz);
+    case 2: return launch_run_w<MODEL, 2>(ctx, kind, b, e, R, rz);
+    case 4: return launch_run_w<MODEL, 4>(ctx, kind, b, e, R, rz);
+    default: return launch_run_w<MODEL, 8>(ctx, kind, b, e, R, rz);
+    }
+}
+
+template <int MODEL, int WMAX>
+int launch_init_t(pdg_ctx *ctx, int kind)
+{
+    const InitSmem L = init_smem_layout(ctx->P.p, ctx->P.W, tri_bytes_for(ctx->P.ll_cap));
+    int rc;
+    if ((rc = set_smem(ctx, k_init_logl<MODEL, WMAX>, L.total))) return rc;
+    k_init_logl<MODEL, WMAX><<<(unsigned)ctx->P.n_chains, 32, L.total, ctx->stream>>>(ctx->P, kind);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PDG_OK;
+}
+
+template <int MODEL>
+int launch_init_m(pdg_ctx *ctx, int kind)
+{
+    switch (ctx->wmax) {
+    case 1: return launch_init_t<MODEL, 1>(ctx, kind);
+    case 2: return launch_init_t<MODEL, 2>(ctx, kind);
+    case 4: return launch_init_t<MODEL, 4>(ctx, kind);
+    default: return launch_init_t<MODEL, 8>(ctx, kind);
+    }
+}
+
+template <int MODEL, int WMAX>
+int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
+{
+    long long grid = n_sets < ctx->P.n_chains ? n_sets : ctx->P.n_chains;
+#ifdef PDG_LANE_SMEM
+    const int sm = PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+#else
+    const int sm = tri_bytes_for(ctx->P.ll_cap) + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
+#endif
+    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PDG_OK;
+}
+
+template <int MODEL>
+int launch_score_m(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
+{
+    switch (ctx->wmax) {
+    case 1: return launch_score_t<MODEL, 1>(ctx, d_bits, n_sets, d_out, d_err);
+    case 2: return launch_score_t<MODEL, 2>(ctx, d_bits, n_sets, d_out, d_err);
+    case 4: return launch_score_t<MODEL, 4>(ctx, d_bits, n_sets, d_out, d_err);
+    default: return launch_score_t<MODEL, 8>(ctx, d_bits, n_sets, d_out, d_err);
+    }
+}
+
+
+}  // namespace
+
+#define PDG_CAT2(a, b) a##b
+#define PDG_CAT(a, b) PDG_CAT2(a, b)
+
+int PDG_CAT(pdg_launch_run_, PDG_TU_NAME)(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long rz)
+{
+    return launch_run_m<PDG_TU_MODEL>(ctx, kind, b, e, R, rz);
+}
+int PDG_CAT(pdg_launch_init_, PDG_TU_NAME)(pdg_ctx *ctx, int kind) { return launch_init_m<PDG_TU_MODEL>(ctx, kind); }
+int PDG_CAT(pdg_launch_score_, PDG_TU_NAME)(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
+{
+    return launch_score_m<PDG_TU_MODEL>(ctx, d_bits, n_sets, d_out, d_err);
+}

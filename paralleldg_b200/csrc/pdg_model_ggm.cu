@@ -1,0 +1,4 @@
+// ggm instantiations of the MH, logl[0] and batch-scorer kernels (see pdg_model.inl)
+#define PDG_TU_MODEL PDG_MODEL_GGM
+#define PDG_TU_NAME ggm
+#include "pdg_model.inl"

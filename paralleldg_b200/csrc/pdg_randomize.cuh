@@ -113,6 +113,7 @@ __device__ __forceinline__ void build_derived(const PT &P, long long chain, int 
     __syncwarp();
 }
 
+#ifdef PDG_DEFINE_GLOBAL_KERNELS
 __global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long chain_begin, long long chain_count)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(32) k_build_derived(PdgParams P, long long cha
     if (c >= chain_count) return;
     build_derived(P, chain_begin + c, threadIdx.x, (int *)smem);
 }
+#endif
 
 // The fields of PdgParams the randomiser needs, passed BY VALUE: randomize_chain is out of line (it
 // is cold inside the MH kernel and would bloat its loop body) and taking the address of the kernel
@@ -142,7 +144,7 @@ __device__ __forceinline__ RandArgs rand_args(const PdgParams &P)
 
 // randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
 // shared memory.  Works on the global-memory state and rebuilds N and the CSR at the end.
-__device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long long chain, u32 iter,
+static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long long chain, u32 iter,
                                              unsigned char *smem, int lane)
 {
     const int p = P.p, W = P.W;
@@ -459,8 +461,10 @@ __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long lon
     build_derived(P, chain, lane, (int *)(smem + L.off_deg32));
 }
 
+#ifdef PDG_DEFINE_GLOBAL_KERNELS
 __global__ void __launch_bounds__(32) k_randomize(PdgParams P, RandScratch Z, u32 iter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     randomize_chain(rand_args(P), Z, blockIdx.x, iter, smem, threadIdx.x);
 }
+#endif

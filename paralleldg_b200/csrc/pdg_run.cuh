@@ -29,43 +29,6 @@
 #define PT_FLUSH
 #endif
 
-struct RunSmem {
-    int off_tri, off_idx, off_sub, off_leaf, off_bnd, off_partner, off_mvU, off_mvUadj, off_csr_off, off_csr_adj,
-        off_M, off_N, off_T, off_lidx, off_tmpU, off_tmpA, off_cnt, total;
-};
-
-__host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state, int tri_bytes)
-{
-    RunSmem s;
-    int o = 0;
-    const int np32 = 2 * W + 2;
-    const int a2 = ((p + 2) * 2 + 15) / 16 * 16;
-#ifdef PDG_LANE_SMEM
-    s.off_tri = o;      o += PDG_KTRI * 32 * 8;          // lane-private triangles (alias the 32x32 warp triangle)
-    s.off_lidx = o;     o += PDG_KT * 32 * 2;
-#else
-    s.off_tri = o;      o += tri_bytes;
-    s.off_lidx = o;     o += PDG_KT * 32 * 2;            // lane-private index columns (multi-word keys)
-#endif
-    s.off_sub = o;      o += W * 8;
-    s.off_M = o;        o += smem_state ? p * W * 8 : 0;
-    s.off_N = o;        o += smem_state ? p * W * 8 : 0;
-    s.off_T = o;        o += smem_state ? p * W * 8 : 0;     // adjacency bit-matrix of the latent tree
-    s.off_leaf = o;     o += (np32 * 4 + 15) / 16 * 16;
-    s.off_bnd = o;      o += (np32 * 4 + 15) / 16 * 16;
-    s.off_idx = o;      o += a2;
-    s.off_partner = o;  o += a2;
-    s.off_mvU = o;      o += a2;
-    s.off_mvUadj = o;   o += a2;
-    s.off_csr_off = o;  o += a2;
-    s.off_csr_adj = o;  o += 2 * a2;
-    s.off_tmpU = o;     o += smem_state ? 0 : a2;      // unsorted boundary of the neighbourhood-driven scan
-    s.off_tmpA = o;     o += smem_state ? 0 : a2;
-    s.off_cnt = o;      o += 16;
-    s.total = (o + 15) / 16 * 16;
-    return s;
-}
-
 // Scores of up to 32 complete sets, one per lane (`need` lanes carry a key each).
 //   GGM, |X| <= PDG_KT : every lane factorises its own set (no communication)
 //   otherwise          : memo table; the warp resolves the misses one after the other with the
@@ -515,7 +478,8 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
                     P.rec[ro] = h;
 #pragma unroll
                     for (int w = 0; w < WMAX; ++w) if (w < W) { P.rec_bits[ro * 2 * W + w] = Cw[w]; P.rec_bits[ro * 2 * W + W + w] = Aw[w]; }
-                } else errflag |= ERR_OVERFLOW;
+                } else if (P.rec_cap > 0) errflag |= ERR_OVERFLOW;      // rec_cap == 0: recording is off
+                if (k + j + 1 > 2147483647LL) errflag |= ERR_OVERFLOW;     // pdg_update.k is 32 bits wide
             }
             u32 rem = am;
             while (rem) {                                   // :269,:301 log_p += ... in proposal order

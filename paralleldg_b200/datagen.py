@@ -102,9 +102,9 @@ def ggm_ar_data(p, n, seed, max_bandwidth=5, rho=0.9, sigma2=1.0):
 
 def loglin_ar_data(p, n, seed, max_bandwidth=5, levels=2, lam=1.0):
     """Discrete data Markov w.r.t. a random AR graph, by ancestral sampling along its junction
-    tree with Dirichlet(lam / cells) clique tables made consistent on the separators (the
-    scalable equivalent of discrete_dec_log_linear.py:108-201,276-318, which materialises the
-    full joint table).  Returns (data [n, p] uint8, levels [p], adjacency)."""
+    tree with hyper-consistent Dirichlet clique tables (discrete_dec_log_linear.py:108-201; the
+    reference then materialises the full joint table, :276-318, which is infeasible beyond p ~ 20:
+    sampling clique by clique along the junction tree draws from the same joint distribution).  Returns (data [n, p] uint8, levels [p], adjacency)."""
     rng = np.random.RandomState(seed)
     adj = sample_random_AR_graph(p, max_bandwidth, rng)
     g = nx.from_numpy_array(np.asarray(adj))
@@ -125,7 +125,10 @@ def loglin_ar_data(p, n, seed, max_bandwidth=5, levels=2, lam=1.0):
         k_new = int(np.prod(lv[new]))
         k_old = int(np.prod(lv[old])) if old else 1
         # conditional table P(new | old), one Dirichlet row per parent configuration
-        tab = rng.dirichlet(np.full(k_new, lam / max(k_new, 1) + 0.5), size=k_old)
+        # hyper-consistent recipe (discrete_dec_log_linear.py:108-201): the first clique's table is
+        # Dirichlet(lam / cells, ...) and, for every configuration of the separator, the conditional table
+        # of the new variables is Dirichlet(lam / cells_new, ...) (:184-189, `d * sep_marg`)
+        tab = rng.dirichlet(np.full(k_new, lam / float(k_new)), size=k_old)
         cum = np.cumsum(tab, axis=1)
         if old:
             code = np.zeros(n, dtype=np.int64)

@@ -121,6 +121,18 @@ class _GPUScored(SequentialJTDistribution):
     batch scorer (pdg_score_sets).  Memoised in `self.cache` like the reference."""
     model_kind = 0
     cache = None
+    _token_counter = [0]
+
+    def _model_changed(self):
+        """init_model was called: everything derived from the previous model on the GPU side (lgamma
+        tables, the batch-scorer context, uploaded buffers of pooled sampling contexts) is stale"""
+        sc = self.__dict__.pop("_gpu_scorer", None)
+        if sc is not None:
+            sc.close()
+        self.__dict__.pop("_gpu_tables", None)
+        self.__dict__.pop("_gconst", None)
+        _GPUScored._token_counter[0] += 1
+        self._gpu_token = _GPUScored._token_counter[0]
 
     def _scorer(self):
         from paralleldg_b200 import engine
@@ -163,6 +175,7 @@ class UniformJTDistribution(_GPUScored):
     def __init__(self, p):
         self.p = p
         self.cache = {}
+        self._model_changed()
 
     def log_likelihood_partial(self, cliques, separators):
         return 0.0
@@ -193,6 +206,7 @@ class GGMJTPosterior(_GPUScored):
         self.cache = cache
         self.n = X.shape[0]
         self.p = X.shape[1]
+        self._model_changed()
 
     def init_model_from_json(self, sd_json):
         self.init_model(np.asarray(sd_json["data"]), np.asarray(sd_json["parameters"]["D"]),
@@ -240,6 +254,9 @@ class LogLinearJTPosterior(_GPUScored):
         self.data = np.asarray(X)
         self.no_levels = np.array([len(l) for l in levels])
         self.counts = counts
+        if self.no_levels.max() > 256:
+            raise ValueError("the GPU scorer stores level codes as uint8: at most 256 levels per variable")
+        self._model_changed()
 
     def init_model_from_json(self, sd_json):
         self.init_model(np.array(sd_json["data"]), sd_json["parameters"]["cell_alpha"],

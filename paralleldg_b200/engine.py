@@ -56,16 +56,32 @@ def make_context(sd, sd_graph, n_chains, n_samples, seed=0, chain0=0, device=0, 
         pass
     k, a, b = prior_tuple(sd_graph)
     ctx.set_prior(k, a, b)
-    configure_model(ctx, sd)
+    # a pooled context that still holds this very model (same object, no init_model since) keeps its
+    # device buffers: nothing is uploaded again
+    token = (id(sd), getattr(sd, "_gpu_token", None))
+    if getattr(ctx, "_model_token", None) != token or token[1] is None:
+        configure_model(ctx, sd)
+        ctx._model_token = token
     return ctx
 
 
+POOL_LIMIT = 2
+
+
 def release_context(ctx):
+    """back to the pool (at most POOL_LIMIT contexts are kept, the oldest is closed first)"""
     key = getattr(ctx, "_pool_key", None)
     if key is None or key in _POOL:
         ctx.close()
-    else:
-        _POOL[key] = ctx
+        return
+    while len(_POOL) >= POOL_LIMIT:
+        _POOL.pop(next(iter(_POOL))).close()
+    _POOL[key] = ctx
+
+
+def clear_pool():
+    while _POOL:
+        _POOL.popitem()[1].close()
 
 
 def set_bits(sets, W):
@@ -95,6 +111,9 @@ class _Scorer(object):
 
     def score_sets(self, sets):
         return self.ctx.score_sets(set_bits(sets, self.W))
+
+    def close(self):
+        self.ctx.close()
 
 
 def scorer_for(sd):

@@ -38,7 +38,8 @@ def build(sd):
     """tables of one model; cached on the object (they depend only on data shape, levels and
     cell_alpha) so that repeated sampler calls on the same model do not redo ~n lgamma calls per
     table"""
-    key = (id(sd.data), float(sd.cell_alpha), tuple(int(l) for l in sd.no_levels))
+    # (init_model drops `_gpu_tables`, so the key only has to tell apart edits made behind its back)
+    key = (getattr(sd, "_gpu_token", None), sd.data.shape, float(sd.cell_alpha), tuple(int(l) for l in sd.no_levels))
     cached = getattr(sd, "_gpu_tables", None)
     if cached is not None and cached[0] == key:
         return cached[1]
@@ -51,6 +52,8 @@ def _build(sd):
     data = np.asarray(sd.data)
     n, p = data.shape
     levels = np.ascontiguousarray(np.asarray(sd.no_levels, dtype=np.int32))
+    if levels.max() > 256:
+        raise ValueError("level codes are stored as uint8: at most 256 levels per variable")
     if data.min() < 0 or (data.max(axis=0) >= levels).any():
         raise ValueError("level codes must lie in [0, levels)")
     col = np.ascontiguousarray(data.T.astype(np.uint8))

@@ -109,14 +109,22 @@ def sample_chains(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=
     else:
         graph = nx.Graph()
         graph.add_nodes_from(range(p))
-    cap = int(rec_cap) if rec_cap is not None else max(int(n_samples), 64)
-    if not want_updates:
-        cap = 0
+    # update records: the parallel-moves sampler can accept several moves per iteration, so the
+    # default leaves room for two per iteration; a run that still overflows is repeated (runs are
+    # deterministic) with four times the room.  Edge tallies are computed from the records on the
+    # device, so they need them there even when the caller does not want them back.
+    keep_records = want_updates or want_tallies
+    if rec_cap is not None:
+        cap = int(rec_cap)
+    else:
+        cap = max((1 if single_move else 2) * int(n_samples), 64)
+    if not keep_records:
+        cap = 0                                           # recording disabled in the kernel
+    tic = time.time()                                     # (a repeated run counts)
     for attempt in range(6):
         ctx = engine.make_context(sd, sd_graph, n_chains, n_samples, seed=seed, chain0=chain0,
                                   device=device, rec_cap=cap, pooled=pooled)
         try:
-            tic = time.time()
             if replay is not None:
                 _run_replay(ctx, kind, replay, n_chains)
             else:
@@ -129,7 +137,7 @@ def sample_chains(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=
             try:
                 ctx.sync()
             except nat.NativeError as e:
-                if want_updates and "error -5" in str(e) and attempt < 5:
+                if keep_records and e.code == nat.E_OVERFLOW and attempt < 5:
                     cap *= 4                              # record capacity exceeded: rerun (deterministic)
                     continue
                 raise

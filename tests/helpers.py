@@ -18,7 +18,7 @@ def trajectory_fixtures():
     out = []
     for f in sorted(glob.glob(os.path.join(GOLD, "*.npz"))):
         n = os.path.basename(f)[:-4]
-        if n in ("scorers", "forest", "jt_counts") or n.startswith("batch_"):
+        if n in ("scorers", "forest", "jt_counts", "czech_posterior", "generators", "greenthomas") or n.startswith("batch_"):
             continue
         out.append(n)
     return out
@@ -60,9 +60,39 @@ def batch_chain_log(g, c):
         log[k] = g[k][c]
     a, b = int(g["mv_off"][c]), int(g["mv_off"][c + 1])
     for k in BATCH_MV:
-        log[k] = g[k][a:b]
+        if k in g:
+            log[k] = g[k][a:b]
     a, b = int(g["upd_off"][c]), int(g["upd_off"][c + 1])
     for k in BATCH_UPD:
         log[k] = g[k][a:b]
     log["n_updates"] = g["n_updates"][c]
     return log
+
+
+def expand_compact_batch(g):
+    """Narrow-dtype batch fixture (oracle/make_golden.py:loglin_batch_compact) -> the layout of a
+    loglin_batch fixture (what batch_chain_log reads).  Per-move terms may be absent."""
+    if "compact" not in g:
+        return g
+    out = {k: g[k] for k in ("model", "data", "levels", "cell_alpha", "prior", "p", "n_samples", "randomize",
+                             "single", "state_iter", "seeds", "n_updates", "logl")}
+    C, M = g["it_cnt"].shape[0], int(g["n_samples"])
+    out["state_edges"] = g["state_edges"].astype(np.int32)
+    out["state_bits"] = g["state_bits"].astype(np.uint64)
+    for k in ("it_node", "it_mtype_raw", "it_aux"):
+        out[k] = g[k].astype(np.int32)
+    off = np.zeros((C, M + 1), np.int64)
+    off[:, 1:] = np.cumsum(g["it_cnt"].astype(np.int64), axis=1)
+    out["it_off"] = off
+    out["mv_off"] = np.concatenate([[0], np.cumsum(off[:, -1])]).astype(np.int64)
+    out["mv_U"] = g["mv_U"].astype(np.int32)
+    out["mv_Uadj"] = g["mv_Uadj"].astype(np.int32)
+    out["mv_u"] = g["mv_u"]
+    for k in ("mv_dlik", "mv_dprior", "mv_logq"):
+        if k in g:
+            out[k] = g[k]
+    out["upd_off"] = np.concatenate([[0], np.cumsum(g["upd_cnt"])]).astype(np.int64)
+    for k in ("upd_i", "upd_k", "upd_type", "upd_node"):
+        out[k] = g[k].astype(np.int32)
+    out["upd_C"], out["upd_Cadj"] = g["upd_C"], g["upd_Cadj"]
+    return out

@@ -66,6 +66,29 @@ def test_replay_batch_of_reference_chains():
         assert close(res["logl"], log["logl"]).all()
 
 
+@pytest.mark.parametrize("name", ["batch_cfg3_p15_parallel_256chains_M1000", "batch_cfg3_p15_parallel_64chains_M10000"])
+def test_replay_config3_at_scale(name):
+    """Config 3 at scale: 256 distinct reference chains at M = 1000 and 64 at the full
+    M = 10 000, every one replayed through the oracle -- bit-exact jt_updates, 1e-9 log-probability
+    traces (and per-move terms where the fixture carries them)."""
+    from tests.helpers import batch_chain_log, expand_compact_batch
+    g = expand_compact_batch(load_golden(name))
+    m = oracle_model(g)
+    for c in range(len(g["n_updates"])):
+        log = batch_chain_log(g, c)
+        res = orc.run_replay(m, log)
+        assert res["rc"] == 0 and res["k"] == int(log["n_updates"]), c
+        r = res["recs"]
+        assert np.array_equal(r["i"], log["upd_i"]) and np.array_equal(r["k"], log["upd_k"]), c
+        assert np.array_equal(r["type"], log["upd_type"]) and np.array_equal(r["node"], log["upd_node"]), c
+        assert np.array_equal(res["rec_bits"][:, 0], log["upd_C"]) and np.array_equal(res["rec_bits"][:, 1], log["upd_Cadj"]), c
+        mv = res["moves"]
+        assert np.array_equal(mv["U"], log["mv_U"]) and np.array_equal(mv["Uadj"], log["mv_Uadj"]), c
+        if "mv_dlik" in log:
+            assert close(mv["dlik"], log["mv_dlik"]).all() and close(mv["dprior"], log["mv_dprior"]).all(), c
+        assert close(res["logl"], log["logl"]).all(), c
+
+
 def test_scorers_match_reference():
     g = load_golden("scorers")
     for tag, D, delta in (("I1", None, 1.0), ("I5", None, 5.0), ("G3", g["ggm_Dgen"], 3.0)):
