@@ -369,7 +369,8 @@ def czech_posterior_fixture(ref):
     log, traj = rs.trace_chain("parallel", 3000, 100, sd, sdg, seed=77)
     with contextlib.redirect_stdout(io.StringIO()):
         out["one_heatmap_b0"] = np.asarray(traj.empirical_distribution(0).heatmap(), dtype=np.float64)
-        traj.trajectory = None
+        # (same per-index graph list: set_graph_trajectories mutates init_graph in place, a second pass
+        # would start from the final graph)
         out["one_heatmap_b500"] = np.asarray(traj.empirical_distribution(500).heatmap(), dtype=np.float64)
         out["one_size"] = np.asarray(traj.size(0), dtype=np.float64)
         d = tempfile.mkdtemp()
