@@ -120,8 +120,9 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     if (device < 0 || device >= ndev) return PDG_E_ARG;
     pdg_ctx *ctx = new pdg_ctx();
     ctx->device = device;
-    ctx->wpc = n_chains >= 8 ? 8 : (int)n_chains;      // the last CTA may be partial (its barrier counts live warps)
-    if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) ctx->wpc = x; }
+    ctx->wpc = n_chains >= 8 ? 8 : (int)n_chains;      // upper bound; the launcher spreads the chains over all SMs
+    if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) { ctx->wpc = x; ctx->wpc_forced = true; } }
+    { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) ctx->sm_count = n; }
     // 16M slots (256 MB) for one- and two-word keys: the p = 50 hit rate saturates at 2^23; wider
     // keys come with far more distinct cliques (p = 500: 21M per run), 32M slots = 2.7 GB there
     ctx->memo_bits = (p > 128) ? 25 : 24;
@@ -532,13 +533,12 @@ int pdg_sample(pdg_ctx *ctx, int kind, int64_t randomize)
     if (M < 2) return PDG_OK;
     PdgReplayDev R;
     memset(&R, 0, sizeof(R));
-    // One launch per randomisation interval (with the randomiser as its own kernel in between) or
-    // the whole run fused into ONE launch?  Separate launches re-align the chains every `randomize`
-    // iterations, which is what the instruction-fetch-bound GGM / small-table workloads want
-    // (p=50 GGM: 286 vs 279 M proposals/s, p=15 log-linear: 1196 vs 632 M/s); but every launch also
-    // waits for its slowest chain, and when a memo miss costs ~100 iterations (table scans over
-    // many rows) that tail dominates: p=100, n=1e5 log-linear runs 2.4x faster fused.
-    bool fused = ctx->P.model == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192;
+    // The whole run is ONE launch: every warp carries its chain through all iterations and randomises
+    // its own junction tree every `randomize` iterations, so no chain ever waits for another and there is
+    // a single launch tail per run instead of one per randomisation interval (round 1: a third of every
+    // 100-iteration launch was the tail of its slowest CTA).  PDG_FUSED=0 restores one launch per interval
+    // with the randomiser as its own kernel in between.
+    bool fused = true;
     if (const char *v = getenv("PDG_FUSED")) fused = atoi(v) != 0;
     if (!fused) {
         long long it = 1;

@@ -25,7 +25,9 @@ struct pdg_ctx {
     std::vector<void *> model_owned;      // log-linear buffers, freed on a re-set with another shape / destroy
     long long ll_shape[4] = {-1, -1, -1, -1};   // (nrows, n_ktab, hist_cells, n_chains) the buffers were sized for
     int wmax = 1;                         // compile-time word count the kernels are dispatched on
-    int wpc = 8;                          // warps (= chains) per CTA of the MH kernel
+    int wpc = 8;                          // most warps (= chains) per CTA of the MH kernel
+    bool wpc_forced = false;              // PDG_WPC set: use exactly wpc
+    int sm_count = 148;
     bool smem_state = false;
     bool light = false;                   // log-linear model with few rows: the 128-register MH kernel
     int memo_bits = 24;

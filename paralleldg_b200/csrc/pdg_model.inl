@@ -180,27 +180,33 @@ int set_smem(pdg_ctx *ctx, F f, int bytes)
     return PDG_OK;
 }
 
-template <int MODEL, int WMAX, bool SS, bool LIGHT>
+template <int MODEL, int WMAX, bool SS, bool LIGHT, bool DIAG>
 int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
     const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
     const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
     const int per_warp = (randomize > 0 && LR.total > L.total) ? LR.total : L.total;
-    const int wpc = ctx->wpc, sm = per_warp * wpc;
+    // Chains per CTA: one warp each, spread over ALL SMs (1024 chains on 148 SMs -> 7 warps per CTA, 147
+    // CTAs, instead of 128 CTAs of 8); with more chains than fit at once, whole waves of equal size.
+    int wpc = ctx->wpc;
+    if (!ctx->wpc_forced) {
+        const long long resident = (long long)ctx->sm_count * (LIGHT ? 2 : 1);
+        const long long waves = (ctx->P.n_chains + resident * 8 - 1) / (resident * 8);
+        wpc = (int)((ctx->P.n_chains + resident * waves - 1) / (resident * waves));
+        wpc = wpc < 1 ? 1 : wpc > 8 ? 8 : wpc;
+    }
+    const int sm = per_warp * wpc;
     int rc;
-    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT>, sm))) return rc;
+    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG>, sm))) return rc;
     const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
     pdg_time_begin(ctx, ctx->ev_run);
-    // chains of one CTA re-align every `lockstep` iterations (power of two, 0 = never)
+    // chains of one CTA can be re-aligned every `lockstep` iterations (power of two); off by default
     int lockstep = 0;
-    // (not for log-linear models with many rows: a table scan then costs ~100x an iteration and the
-    // other chains of the CTA must not wait for it)
-    if (wpc > 1 && !(MODEL == PDG_MODEL_LOGLIN && ctx->P.nrows > 8192)) {
-        lockstep = 16;
+    if (wpc > 1) {
         if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
-        if (lockstep & (lockstep - 1)) lockstep = 0;
+        if (lockstep < 0 || (lockstep & (lockstep - 1))) lockstep = 0;
     }
-    k_mh_run<MODEL, WMAX, SS, LIGHT><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
+    k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
     pdg_time_end(ctx, ctx->ev_run);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -210,10 +216,16 @@ int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgRepl
 template <int MODEL, int WMAX, bool SS>
 int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
+    // replay logs and the per-proposal diagnostics go through the DIAG build of the kernel
+    const bool diag = R.on || ctx->P.mvlog_cap > 0;
     if constexpr (MODEL == PDG_MODEL_LOGLIN) {
-        if (ctx->light) return launch_run_k<MODEL, WMAX, SS, true>(ctx, kind, b, e, R, randomize);
+        if (ctx->light) {
+            if (diag) return launch_run_k<MODEL, WMAX, SS, true, true>(ctx, kind, b, e, R, randomize);
+            return launch_run_k<MODEL, WMAX, SS, true, false>(ctx, kind, b, e, R, randomize);
+        }
     }
-    return launch_run_k<MODEL, WMAX, SS, false>(ctx, kind, b, e, R, randomize);
+    if (diag) return launch_run_k<MODEL, WMAX, SS, false, true>(ctx, kind, b, e, R, randomize);
+    return launch_run_k<MODEL, WMAX, SS, false, false>(ctx, kind, b, e, R, randomize);
 }
 
 // The chain state lives in shared memory whenever p * W * 16 <= 8192 bytes (pdg_create): always for

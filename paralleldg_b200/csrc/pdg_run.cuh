@@ -29,10 +29,46 @@
 #define PT_FLUSH
 #endif
 
-// Scores of up to 32 complete sets, one per lane (`need` lanes carry a key each).
-//   GGM, |X| <= PDG_KT : every lane factorises its own set (no communication)
-//   otherwise          : memo table; the warp resolves the misses one after the other with the
-//                        cooperative scorers (32-row LDL^T / contingency-table scan)
+// ---- cold paths, out of line -------------------------------------------------------------------
+// The per-iteration path of the MH kernel has to stay small: seven warps of an SM walk it at their
+// own pace and share a 32 KB instruction cache (round 1: 276 KB of fully inlined code, 1.7-2.3 stall
+// cycles per issued instruction waiting for fetches, and a CTA-wide re-alignment barrier to contain
+// it).  Everything an iteration only sometimes needs lives in these functions.  They take the
+// launch parameters by reference: the kernels declare them __grid_constant__, so no local copy of
+// the parameter block is made.
+
+template <int K, int WMAX>
+static __device__ __noinline__ int ggm_lane_cold(const PdgParams &P, unsigned short *lidx, int lane, KeyW<WMAX> XK, int k, double *score)
+{
+    LaneScratch ls; ls.unused = 0; ls.a = nullptr; ls.idx = lidx;
+    double sc = 0.0;
+    const int e = ggm_lane_score_k<K, WMAX>(P, ls, lane, XK.w, k, sc);
+    *score = sc;
+    return e;
+}
+
+template <int WMAX>
+static __device__ __noinline__ int ggm_set_cold(const PdgParams &P, double *tri32, short *idx, double *big, int lane, KeyW<WMAX> XK, double *score)
+{
+    WarpScratch ws; ws.tri32 = tri32; ws.idx = idx; ws.big = big; ws.kbig = P.kbig;
+    double sc = 0.0;
+    const int e = ggm_set_score<WMAX>(P, ws, XK.w, lane, sc);
+    *score = sc;
+    return e;
+}
+
+template <int WMAX>
+static __device__ __noinline__ void memo_insert_cold(const PdgParams &P, KeyW<WMAX> XK, double val)
+{
+    memo_insert<WMAX>(P.memo, XK.w, P.W, val);
+}
+
+// Scores of up to 32 complete sets, one per lane (`need` lanes carry a key each): ONE parallel round
+// trip to the memo table, then
+//   GGM, |X| <= PDG_KT : the lanes that missed factorise their own sets in registers (K = the
+//                        largest missing set of the warp) and publish them
+//   otherwise          : the warp resolves the misses one after the other with the cooperative
+//                        scorers (32-row LDL^T / contingency-table scan)
 // Returns the ERR_* bits raised.
 template <int MODEL, int WMAX, int NB = 4>
 __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
@@ -46,31 +82,33 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     int kq = 0;
 #pragma unroll
     for (int w = 0; w < WMAX; ++w) kq += __popcll(X[w]);
-    if (need) { wk[4] += 1ull; wk[5] += (unsigned long long)kq; }
-    if (MODEL == PDG_MODEL_GGM) {
-        // small sets: one parallel round trip to the memo table for every lane, then the lanes
-        // that missed factorise their own set in registers (K = largest MISSING set) and publish it
-        const bool small = need && kq <= PDG_KT;
-        bool shit = false;
-        double s_small = 0.0;
-        if (small && P.memo_small) shit = memo_lookup<WMAX>(P.memo, X, W, s_small);
-        const bool smiss = small && !shit;
-        double s_new = 0.0;
-        err |= ggm_lane_scores<WMAX>(P, ls, lane, X, smiss ? kq : 0, s_new);
-        if (smiss) {
-            s_small = s_new;
-            if (P.memo_small) memo_insert<WMAX>(P.memo, X, W, s_new);
-            const unsigned long long kk = (unsigned long long)kq, dm = (P.dmode == 2 ? 2ull : 1ull);
-            wk[0] += 8ull * kk * kk * dm;
-            wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * dm;
-            wk[2] += 1ull; wk[3] += kk;
-        }
-        if (small) score = s_small;
-        need = need && !small;
-        __syncwarp();
-    }
-    if (need) hit = memo_lookup<WMAX>(P.memo, X, W, score);
+    if (need) { wk[4] += 1ull; wk[5] += (unsigned long long)kq; hit = memo_lookup<WMAX>(P.memo, X, W, score); }
     u32 miss = __ballot_sync(PDG_FULL, need && !hit);
+    if (miss == 0u) return 0;
+    KeyW<WMAX> XK;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) XK.w[w] = X[w];
+    if (MODEL == PDG_MODEL_GGM) {
+        const bool smiss = need && !hit && kq <= PDG_KT;
+        const int kmax = (int)__reduce_max_sync(PDG_FULL, smiss ? (unsigned)kq : 0u);
+        if (kmax > 0) {
+            double s_new = 0.0;
+            const int kk_ = smiss ? kq : 0;
+            if (kmax <= 4 && !PDG_NO_K4) err |= ggm_lane_cold<4, WMAX>(P, ls.idx, lane, XK, kk_, &s_new);
+            else if (kmax <= 8) err |= ggm_lane_cold<8, WMAX>(P, ls.idx, lane, XK, kk_, &s_new);
+            else err |= ggm_lane_cold<12, WMAX>(P, ls.idx, lane, XK, kk_, &s_new);
+            if (smiss) {
+                score = s_new; hit = true;
+                memo_insert_cold<WMAX>(P, XK, s_new);
+                const unsigned long long kk = (unsigned long long)kq, dm = (P.dmode == 2 ? 2ull : 1ull);
+                wk[0] += 8ull * kk * kk * dm;
+                wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * dm;
+                wk[2] += 1ull; wk[3] += kk;
+            }
+            __syncwarp();
+            miss = __ballot_sync(PDG_FULL, need && !hit);
+        }
+    }
     while (miss) {
         int src = __ffs((int)miss) - 1;
         if (MODEL == PDG_MODEL_LOGLIN) {
@@ -80,16 +118,17 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
             src = __ffs((int)__ballot_sync(PDG_FULL, need && !hit && kq == kmax)) - 1;
         }
         u64 Y[WMAX];
+        KeyW<WMAX> YK;
 #pragma unroll
-        for (int w = 0; w < WMAX; ++w) Y[w] = __shfl_sync(PDG_FULL, X[w], src);
+        for (int w = 0; w < WMAX; ++w) { Y[w] = __shfl_sync(PDG_FULL, X[w], src); YK.w[w] = Y[w]; }
         double sc = 0.0;
         int e;
         LlTable tab; tab.cells = 0u; tab.k = 0;
-        if (MODEL == PDG_MODEL_GGM) e = ggm_set_score<WMAX>(P, ws, Y, lane, sc);
+        if (MODEL == PDG_MODEL_GGM) e = ggm_set_cold<WMAX>(P, ws.tri32, ws.idx, ws.big, lane, YK, &sc);
         else e = loglin_set_score<WMAX, NB>(P, ws, slot, Y, lane, sc, tab);
         err |= e;
         if (lane == 0) {
-            if (!e) memo_insert<WMAX>(P.memo, Y, W, sc);
+            if (!e) memo_insert_cold<WMAX>(P, YK, sc);
             int k = 0;
 #pragma unroll
             for (int w = 0; w < WMAX; ++w) k += __popcll(Y[w]);
@@ -116,10 +155,11 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
                 if (!subs) break;
                 const int zs = __ffs((int)subs) - 1;
                 u64 Zk[WMAX];
+                KeyW<WMAX> ZK;
 #pragma unroll
-                for (int w = 0; w < WMAX; ++w) Zk[w] = __shfl_sync(PDG_FULL, X[w], zs);
+                for (int w = 0; w < WMAX; ++w) { Zk[w] = __shfl_sync(PDG_FULL, X[w], zs); ZK.w[w] = Zk[w]; }
                 const double sz = loglin_subset_score<WMAX>(P, ws, tab, Zk, lane);
-                if (lane == 0) { memo_insert<WMAX>(P.memo, Zk, W, sz); wk[7] += 1ull; }
+                if (lane == 0) { memo_insert_cold<WMAX>(P, ZK, sz); wk[7] += 1ull; }
                 bool sm = need && !hit;
 #pragma unroll
                 for (int w = 0; w < WMAX; ++w) sm = sm && (X[w] == Zk[w]);
@@ -131,17 +171,69 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     return err;
 }
 
+// the rare proposal shapes (parallel_moves.py:138-139, :184-187): an empty subtree connects to one
+// random tree node; a subtree of one or two tree nodes offers one disconnect.  Lane 0 writes the move.
+static __device__ __noinline__ int special_move(const u32 *s_sub32, int nw32, int mtype, int msub, int p, u32 r2, int replay_on,
+                                                int aux, short *s_mvU, short *s_mvUadj)
+{
+    int err = 0;
+    if (mtype == 0) {                         // pm:138-139 one random tree node
+        s_mvU[0] = (short)(replay_on ? aux : (int)__umulhi(r2, (u32)p));
+        s_mvUadj[0] = -1;
+    } else {
+        int a = -1, b = -1;
+        for (int i = 0; i < nw32; ++i) {
+            u32 x = s_sub32[i];
+            while (x) { const int t = i * 32 + __ffs((int)x) - 1; x &= x - 1; if (a < 0) a = t; else if (b < 0) b = t; }
+        }
+        if (msub == 1) { s_mvU[0] = (short)a; s_mvUadj[0] = -1; }          // pm:186-187
+        else {                                  // pm:184-185 one of the two leaves
+            int pick;
+            if (replay_on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) err = ERR_REPLAY; }
+            else pick = (int)(r2 >> 31);
+            s_mvU[0] = (short)(pick ? b : a);
+            s_mvUadj[0] = (short)(pick ? a : b);
+        }
+    }
+    return err;
+}
+
+// (re)loads the tree of a chain -- and, for small p, its whole state plus the adjacency bit-matrix of
+// the tree -- into the warp's shared memory: at kernel start and after every randomisation
+template <bool SMEM_STATE>
+static __device__ __noinline__ void reload_chain_state(const PdgParams &P, unsigned char *smem, long long chain, int lane)
+{
+    const int p = P.p, W = P.W;
+    const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
+    unsigned short *s_off = (unsigned short *)(smem + L.off_csr_off);
+    unsigned short *s_adj = (unsigned short *)(smem + L.off_csr_adj);
+    for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
+    for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
+    if (SMEM_STATE) {
+        const u64 *Mg = P.M + (size_t)chain * p * W, *Ng = P.N + (size_t)chain * p * W;
+        u64 *Mc = (u64 *)(smem + L.off_M), *Nc = (u64 *)(smem + L.off_N), *Tt = (u64 *)(smem + L.off_T);
+        for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; Tt[i] = 0ull; }
+        __syncwarp();
+        for (int t = lane; t < p; t += 32)
+            for (int e = s_off[t]; e < s_off[t + 1]; ++e) { const int a = s_adj[e]; Tt[(size_t)t * W + (a >> 6)] |= 1ull << (a & 63); }
+    }
+    __syncwarp();
+}
+
 // LIGHT (log-linear models with few rows): one 512-row block per scan pass and a 128-register budget,
-// so that two CTAs (16 chains) share an SM when a GPU runs more than 1184 chains
-template <int MODEL, int WMAX, bool SMEM_STATE, bool LIGHT = false>
-__global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int kind, long long it_begin, long long it_end,
-                                                PdgReplayDev R, int lockstep, RandScratch Z, long long randomize, int smem_per_warp)
+// so that two CTAs share an SM when a GPU runs more than 1184 chains.
+// DIAG: the variant that can follow a replay log of the reference and keep the per-proposal
+// diagnostics; the production kernels carry neither.
+template <int MODEL, int WMAX, bool SMEM_STATE, bool LIGHT, bool DIAG>
+__global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin,
+                                                long long it_end, const __grid_constant__ PdgReplayDev R, int lockstep,
+                                                RandScratch Z, long long randomize, int smem_per_warp)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
     const int p = P.p, W = P.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const long long chain = (long long)blockIdx.x * wpc + warp;
-    if (chain >= P.n_chains) return;                       // (the re-alignment barrier below counts live warps only)
+    if (chain >= P.n_chains) return;                       // (the optional re-alignment barrier counts live warps only)
     const int live_threads = 32 * (int)(((long long)(blockIdx.x + 1) * wpc <= P.n_chains) ? wpc : (P.n_chains - (long long)blockIdx.x * wpc));
     const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
     unsigned char *smem = smem_all + (size_t)warp * smem_per_warp;
@@ -172,32 +264,26 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
     u64 *Mc = SMEM_STATE ? (u64 *)(smem + L.off_M) : Mg;
     u64 *Nc = SMEM_STATE ? (u64 *)(smem + L.off_N) : Ng;
     u64 *Tt = (u64 *)(smem + L.off_T);                      // only with SMEM_STATE
-    for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
-    for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
-    if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; }
-    if (SMEM_STATE) {
-        __syncwarp();
-        for (int i = lane; i < p * W; i += 32) Tt[i] = 0ull;
-        __syncwarp();
-        for (int t = lane; t < p; t += 32)
-            for (int e = s_off[t]; e < s_off[t + 1]; ++e) { const int a = s_adj[e]; Tt[(size_t)t * W + (a >> 6)] |= 1ull << (a & 63); }
-    }
-    __syncwarp();
+
+    reload_chain_state<SMEM_STATE>(P, smem, chain, lane);
 
     const u32 gchain = P.chain0 + (u32)chain;
     long long k = P.kcount[chain];
     long long nrec = P.nrec[chain];
     double logl_prev = P.logl[(size_t)chain * P.n_samples + it_begin - 1];
+    double lbuf = 0.0;                  // logl of iteration (block start + lane): stored 32 at a time, coalesced
+    u32 rb0 = 0u, rb1 = 0u, rb2 = 0u, rb3 = 0u;     // Philox draws of iteration (block start + lane)
     int errflag = 0;
     unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
     const u32 lt = (1u << lane) - 1u;
     const int nw32 = (p + 31) >> 5;
+    const bool replay_on = DIAG && R.on;
     PT_DECL
 
     for (long long it = it_begin; it < it_end; ++it) {
-        // chains of one CTA re-align every `lockstep` iterations: the loop body is larger than the
-        // L1.5 instruction cache, loosely in step the warps share its fetches instead of each
-        // streaming it (measured: fused single-launch runs go from 228 to 293 M proposals/s)
+        const int sl = (int)((it - it_begin) & 31);
+        // optional re-alignment of the chains of a CTA (PDG_LOCKSTEP; off by default: the loop body
+        // now fits the instruction cache and nothing is gained by marching in step)
         if (lockstep && ((it - it_begin) & (lockstep - 1)) == 0) asm volatile("bar.sync 1, %0;" :: "r"(live_threads) : "memory");
         // ---- junction-tree randomisation every `randomize` iterations (mh_parallel.py:226-228),
         // fused here so that a whole run is ONE launch and no chain ever waits for another.  The
@@ -209,28 +295,23 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
             if (!SMEM_STATE) __threadfence();       // rows flipped with L2 atomics: nothing stale in L1 for the randomiser's loads
             randomize_chain(rand_args(P), Z, chain, (u32)it, smem, lane);
             __syncwarp();
-            for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
-            for (int i = lane; i < 2 * (p - 1); i += 32) s_adj[i] = P.csr_adj[(size_t)chain * 2 * p + i];
-            if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mc[i] = Mg[i]; Nc[i] = Ng[i]; }
-        if (SMEM_STATE) {
-            __syncwarp();
-            for (int i = lane; i < p * W; i += 32) Tt[i] = 0ull;
-            __syncwarp();
-            for (int t = lane; t < p; t += 32)
-                for (int e = s_off[t]; e < s_off[t + 1]; ++e) { const int a = s_adj[e]; Tt[(size_t)t * W + (a >> 6)] |= 1ull << (a & 63); }
+            reload_chain_state<SMEM_STATE>(P, smem, chain, lane);
         }
-            __syncwarp();
-        }
-        // ---- draws (mh_parallel.py:230-231) -------------------------------------------------
+        // ---- draws (mh_parallel.py:230-231): one Philox block per iteration, 32 iterations at a time
+        // (lane l draws for iteration it + l), handed out by shuffle
         int node, mtype, aux = -1;
-        u32 r[4] = {0u, 0u, 0u, 0u};
-        if (R.on) {
+        u32 r2 = 0u, r3 = 0u;
+        if (replay_on) {
             const size_t o = (size_t)chain * R.n_samples + it;
             node = R.it_node[o]; mtype = R.it_mtype[o]; aux = R.it_aux[o];
         } else {
-            philox4x32_10(gchain, (u32)it, TAG_ITER, 0u, P.seed_lo, P.seed_hi, r);
-            node = (int)__umulhi(r[0], (u32)p);
-            mtype = (int)(r[1] >> 31);
+            if (sl == 0) {
+                u32 r[4];
+                philox4x32_10(gchain, (u32)(it + lane), TAG_ITER, 0u, P.seed_lo, P.seed_hi, r);
+                rb0 = r[0]; rb1 = r[1]; rb2 = r[2]; rb3 = r[3];
+            }
+            node = (int)__umulhi(__shfl_sync(PDG_FULL, rb0, sl), (u32)p);
+            mtype = (int)(__shfl_sync(PDG_FULL, rb1, sl) >> 31);
         }
         // (state in global memory is updated with atomics in L2: read it there, never through L1)
         if (lane < W) s_sub[lane] = SMEM_STATE ? Nc[(size_t)node * W + lane] : __ldcg(&Nc[(size_t)node * W + lane]);
@@ -336,30 +417,12 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
         const u32 *set = (mtype == 0) ? s_bnd : s_leaf;
         if (special) {
             nm = 1;
-            if (lane == 0) {
-                if (mtype == 0) {                         // pm:138-139 one random tree node
-                    s_mvU[0] = (short)(R.on ? aux : (int)__umulhi(r[2], (u32)p));
-                    s_mvUadj[0] = -1;
-                } else {
-                    int a = -1, b = -1;
-                    for (int i = 0; i < nw32; ++i) {
-                        u32 x = s_sub32[i];
-                        while (x) { const int t = i * 32 + __ffs((int)x) - 1; x &= x - 1; if (a < 0) a = t; else if (b < 0) b = t; }
-                    }
-                    if (msub == 1) { s_mvU[0] = (short)a; s_mvUadj[0] = -1; }          // pm:186-187
-                    else {                                  // pm:184-185 one of the two leaves
-                        int pick;
-                        if (R.on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) errflag |= ERR_REPLAY; }
-                        else pick = (int)(r[2] >> 31);
-                        s_mvU[0] = (short)(pick ? b : a);
-                        s_mvUadj[0] = (short)(pick ? a : b);
-                    }
-                }
-            }
+            if (!replay_on) r2 = __shfl_sync(PDG_FULL, rb2, sl);
+            if (lane == 0) errflag |= special_move(s_sub32, nw32, mtype, msub, p, r2, replay_on ? 1 : 0, aux, s_mvU, s_mvUadj);
             nfwd = (mtype == 1 && msub == 2) ? 2 : 1;
             if (kind == PDG_KIND_PARALLEL && mtype == 1 && msub == 2) logq = -0.6931471805599453;   // :277
         } else if (kind == PDG_KIND_PARALLEL) {
-            if (R.on) {
+            if (replay_on) {
                 // the reference's ORDER (python set iteration); the SET is checked against ours
                 const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
                 const long long cnt = R.it_off[(size_t)chain * (R.n_samples + 1) + it + 1] - o;
@@ -374,12 +437,13 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
         } else {
             // single move: moves[0] after np.random.shuffle (:87,:95 / :128,:138)
             int U, Ua;
-            if (R.on) {
+            if (replay_on) {
                 const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
                 U = R.mv_U[o]; Ua = R.mv_Uadj[o];
                 if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
             } else {
-                const int pick = nm > 1 ? (int)__umulhi(r[3], (u32)nm) : 0;
+                r3 = __shfl_sync(PDG_FULL, rb3, sl);
+                const int pick = nm > 1 ? (int)__umulhi(r3, (u32)nm) : 0;
                 U = s_mvU[pick]; Ua = s_mvUadj[pick];
             }
             __syncwarp();
@@ -453,53 +517,60 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(PdgParams P, int 
                 const double dl = log_p2 - log_p1, dp = log_g2 - log_g1;
                 const double tot = (dl + dp) + logq;
                 double u;
-                if (R.on) u = R.mv_u[R.it_off[(size_t)chain * (R.n_samples + 1) + it] + j];
+                if (replay_on) u = R.mv_u[R.it_off[(size_t)chain * (R.n_samples + 1) + it] + j];
                 else u = draw_unif(P.seed_lo, P.seed_hi, gchain, (u32)it, TAG_MOVE, (u32)U);
                 const double e = exp(tot);
                 acc = u <= (e < 1.0 ? e : 1.0);                                                 // :268,:300
                 delta = dl + dp;
-                const long long kk = k + j + 1;
-                if (P.mvlog_cap && kk - 1 < P.mvlog_cap) {
-                    const size_t o = (size_t)chain * P.mvlog_cap + (kk - 1);
-                    P.ml_dlik[o] = dl; P.ml_dprior[o] = dp; P.ml_logq[o] = logq; P.ml_u[o] = u;
-                    P.ml_acc[o] = acc ? 1 : 0; P.ml_U[o] = U;
+                if (DIAG) {
+                    const long long kk = k + j + 1;
+                    if (P.mvlog_cap && kk - 1 < P.mvlog_cap) {
+                        const size_t o = (size_t)chain * P.mvlog_cap + (kk - 1);
+                        P.ml_dlik[o] = dl; P.ml_dprior[o] = dp; P.ml_logq[o] = logq; P.ml_u[o] = u;
+                        P.ml_acc[o] = acc ? 1 : 0; P.ml_U[o] = U;
+                    }
                 }
             }
             PT(5)
             // accepted proposals in order: record append, running log-probability, bit flips
             const u32 am = __ballot_sync(PDG_FULL, acc);
-            if (acc) {
-                const long long slot_r = nrec + __popc(am & lt);
-                if (slot_r < P.rec_cap) {
-                    const size_t ro = (size_t)chain * P.rec_cap + slot_r;
-                    pdg_update h;
-                    h.i = (int)it; h.k = (int)(k + j + 1); h.node = (unsigned short)node; h.U = (unsigned short)U;
-                    h.Uadj = (short)Ua; h.type = (unsigned char)mtype; h.pad = 0;
-                    P.rec[ro] = h;
+            if (am) {
+                if (acc) {
+                    const long long slot_r = nrec + __popc(am & lt);
+                    if (slot_r < P.rec_cap) {
+                        const size_t ro = (size_t)chain * P.rec_cap + slot_r;
+                        pdg_update h;
+                        h.i = (int)it; h.k = (int)(k + j + 1); h.node = (unsigned short)node; h.U = (unsigned short)U;
+                        h.Uadj = (short)Ua; h.type = (unsigned char)mtype; h.pad = 0;
+                        P.rec[ro] = h;
 #pragma unroll
-                    for (int w = 0; w < WMAX; ++w) if (w < W) { P.rec_bits[ro * 2 * W + w] = Cw[w]; P.rec_bits[ro * 2 * W + W + w] = Aw[w]; }
-                } else if (P.rec_cap > 0) errflag |= ERR_OVERFLOW;      // rec_cap == 0: recording is off
-                if (k + j + 1 > 2147483647LL) errflag |= ERR_OVERFLOW;     // pdg_update.k is 32 bits wide
+                        for (int w = 0; w < WMAX; ++w) if (w < W) { P.rec_bits[ro * 2 * W + w] = Cw[w]; P.rec_bits[ro * 2 * W + W + w] = Aw[w]; }
+                    } else if (P.rec_cap > 0) errflag |= ERR_OVERFLOW;      // rec_cap == 0: recording is off
+                    if (k + j + 1 > 2147483647LL) errflag |= ERR_OVERFLOW;     // pdg_update.k is 32 bits wide
+                }
+                u32 rem = am;
+                while (rem) {                                   // :269,:301 log_p += ... in proposal order
+                    const int src = __ffs((int)rem) - 1;
+                    rem &= rem - 1;
+                    log_p += __shfl_sync(PDG_FULL, delta, src);
+                }
+                nrec += __popc(am);
+                __syncwarp();
+                if (acc) {                                      // junction_tree.py:78-100 connect / disconnect
+                    atomicXor(&Mc[(size_t)U * W + (node >> 6)], 1ull << (node & 63));
+                    atomicXor(&Nc[(size_t)node * W + (U >> 6)], 1ull << (U & 63));
+                }
+                if (!SMEM_STATE) __threadfence();           // the bit flips are performed before any lane reads the rows again
+                __syncwarp();
             }
-            u32 rem = am;
-            while (rem) {                                   // :269,:301 log_p += ... in proposal order
-                const int src = __ffs((int)rem) - 1;
-                rem &= rem - 1;
-                log_p += __shfl_sync(PDG_FULL, delta, src);
-            }
-            nrec += __popc(am);
-            __syncwarp();
-            if (acc) {                                      // junction_tree.py:78-100 connect / disconnect
-                atomicXor(&Mc[(size_t)U * W + (node >> 6)], 1ull << (node & 63));
-                atomicXor(&Nc[(size_t)node * W + (U >> 6)], 1ull << (U & 63));
-            }
-            if (!SMEM_STATE && am) __threadfence();         // the bit flips are performed before any lane reads the rows again
-            __syncwarp();
         }
         PT(6)
         k += nm;
         logl_prev = logl_prev + log_p;                      // :304 running sum
-        if (lane == 0) P.logl[(size_t)chain * P.n_samples + it] = logl_prev;
+        if (lane == sl) lbuf = logl_prev;
+        if (sl == 31 || it + 1 == it_end) {
+            if (lane <= sl) P.logl[(size_t)chain * P.n_samples + (it - sl) + lane] = lbuf;
+        }
     }
     __syncwarp();
     PT_FLUSH
