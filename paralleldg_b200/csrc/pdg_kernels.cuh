@@ -144,6 +144,7 @@ __device__ __forceinline__ bool memo_lookup(const MemoTable &T, const u64 (&X)[W
 {
     if (WMAX == 1) {
         u32 h = (u32)mix64(X[0]) & T.mask;
+#pragma unroll 1
         for (int pr = 0; pr < MEMO_PROBES; ++pr) {
             const ulonglong2 e = __ldcg(&T.kv[h]);
             if (e.x == X[0]) {
@@ -159,6 +160,7 @@ __device__ __forceinline__ bool memo_lookup(const MemoTable &T, const u64 (&X)[W
         const u64 hh = key_hash<WMAX>(X, W);
         const u64 tag = hh | 1ull;
         u32 h = (u32)(hh >> 32) & T.mask;
+#pragma unroll 1
         for (int pr = 0; pr < MEMO_PROBES; ++pr) {
             const u64 t = __ldcg(&T.tag[h]);
             if (t == 0ull) return false;
@@ -189,6 +191,7 @@ __device__ __forceinline__ void memo_insert(const MemoTable &T, const u64 (&X)[W
     const u64 vb = (u64)__double_as_longlong(val);
     if (WMAX == 1) {
         u32 h = (u32)mix64(X[0]) & T.mask;
+#pragma unroll 1
         for (int pr = 0; pr < MEMO_PROBES; ++pr) {
             const u64 old = atomicCAS(&T.kv[h].x, 0ull, X[0]);
             if (old == 0ull || old == X[0]) { __stcg(&T.kv[h].y, vb); return; }
@@ -198,6 +201,7 @@ __device__ __forceinline__ void memo_insert(const MemoTable &T, const u64 (&X)[W
         const u64 hh = key_hash<WMAX>(X, W);
         const u64 tag = hh | 1ull;
         u32 h = (u32)(hh >> 32) & T.mask;
+#pragma unroll 1
         for (int pr = 0; pr < MEMO_PROBES; ++pr) {
             const u64 old = atomicCAS(&T.tag[h], 0ull, tag);
             if (old == 0ull) {
@@ -489,6 +493,79 @@ __device__ __forceinline__ int ggm_lane_scores(const PdgParams &P, const LaneScr
     if (kmax <= 4 && !PDG_NO_K4) return ggm_lane_score_k<4, WMAX>(P, ls, lane, X, k, score);
     if (kmax <= 8) return ggm_lane_score_k<8, WMAX>(P, ls, lane, X, k, score);
     return ggm_lane_score_k<12, WMAX>(P, ls, lane, X, k, score);
+}
+
+// ---- lane-private scorer, rolled (the one the MH kernel and the batch scorer use) ---------------
+// Same arithmetic as ggm_lane_score_k -- right-looking LDL^T in ascending vertex order, log of the
+// product of the pivots -- hence the same bits for every set, but with ROLLED loops over a
+// lane-private triangle in shared memory: ~150 instructions of code whatever the set size, and the
+// number executed follows the actual |X| (the unrolled register variants run K = 4 / 8 / 12 padded,
+// 800 / 1800 / 3100 instructions each, and need ~200 registers: with them inlined the MH loop neither
+// fits the instruction cache nor keeps its own state in registers).  The lanes that need a score are
+// served PDG_SL at a time; element e of slot s sits at tri[e * PDG_SL + s] (the warp's 32-row scratch
+// triangle: 528 doubles >= PDG_SL * PDG_KTRI).
+#define PDG_SL 6
+template <int WMAX>
+__device__ __forceinline__ int ggm_lane_scores_rolled(const PdgParams &P, double *tri, unsigned short *lidx, int lane,
+                                                      const u64 (&X)[WMAX], int k, double &score)
+{
+    const u32 m = __ballot_sync(PDG_FULL, k > 0);
+    const int rank = __popc(m & ((1u << lane) - 1u)), total = __popc(m);
+    const int p = P.p, npass = (P.dmode == 2) ? 2 : 1;
+    int err = 0;
+#pragma unroll 1
+    for (int r0 = 0; r0 < total; r0 += PDG_SL) {
+        if (k > 0 && rank >= r0 && rank < r0 + PDG_SL) {
+            double *a = tri + (rank - r0);
+            unsigned short *idx = lidx + (rank - r0);
+            {
+                int t = 0;
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) {
+                    u64 x = X[w];
+                    while (x) { idx[t * PDG_SL] = (unsigned short)(w * 64 + __ffsll((long long)x) - 1); x &= x - 1; ++t; }
+                }
+            }
+            double ld[2] = {0.0, 0.0};
+            bool ok = true;
+#pragma unroll 1
+            for (int pass = 0; pass < npass; ++pass) {
+                const double *__restrict__ mat = pass ? P.Dm : P.A;
+#pragma unroll 1
+                for (int i = 0, e = 0; i < k; ++i) {
+                    const double *row = mat + (size_t)idx[i * PDG_SL] * p;
+                    for (int l = 0; l <= i; ++l, ++e) a[e * PDG_SL] = __ldg(row + idx[l * PDG_SL]);
+                }
+                double prod = 1.0;
+#pragma unroll 1
+                for (int j = 0; j < k; ++j) {
+                    const int jj = (j * (j + 1)) >> 1;
+                    const double d = a[(jj + j) * PDG_SL];
+                    ok = ok && (d > 0.0);
+                    prod *= d;
+                    const double inv = 1.0 / d;
+#pragma unroll 1
+                    for (int i = j + 1; i < k; ++i) {
+                        double *ri = a + (((i * (i + 1)) >> 1)) * PDG_SL;
+                        const double f = ri[j * PDG_SL] * inv;
+                        for (int l = j + 1; l <= i; ++l) ri[l * PDG_SL] -= f * a[(((l * (l + 1)) >> 1) + j) * PDG_SL];
+                    }
+                }
+                double v;
+                if (prod > 1e-280 && prod < 1e280) v = log(prod);
+                else {                           // product left the double range: sum the logs of the pivots instead
+                    v = 0.0;
+                    for (int j = 0; j < k; ++j) v += log(a[(((j * (j + 1)) >> 1) + j) * PDG_SL]);
+                }
+                ld[pass] = v;
+            }
+            if (P.dmode == 1) for (int j = 0; j < k; ++j) ld[1] += P.logDdiag[idx[j * PDG_SL]];
+            score = ggm_score_from(P, k, ld[0], ld[1]);
+            if (!ok) err = ERR_NUMERIC;
+        }
+        __syncwarp();
+    }
+    return err;
 }
 
 template <int WMAX>

@@ -41,9 +41,9 @@ template <int MODEL, int WMAX>
 __device__ __forceinline__ int set_score_any(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
                                              const u64 (&X)[WMAX], int lane, double &sc)
 {
-    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    u32 rs = 0u, rk = 0u;
     double v = 0.0;
-    const int e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, lane == 0, v, wk);
+    const int e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, lane == 0, v, rs, rk);
     sc = __shfl_sync(PDG_FULL, v, 0);
     return __reduce_or_sync(PDG_FULL, (unsigned)e);
 }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     ws.kbig = P.kbig;
     const int slot = blockIdx.x;
     ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
-    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    u32 rs = 0u, rk = 0u;
     for (long long s0 = (long long)blockIdx.x * 32; s0 < n_sets; s0 += (long long)gridDim.x * 32) {
         const long long s = s0 + lane;
         u64 X[WMAX];
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
         for (int w = 0; w < WMAX; ++w) { X[w] = (s < n_sets && w < W) ? bits[(size_t)s * W + w] : 0ull; k += __popcll(X[w]); }
         double sc = 0.0;
         int e = 0;
-        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, s < n_sets && k > 0, sc, wk);
+        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, s < n_sets && k > 0, sc, rs, rk);
         if (e) atomicOr(err, e);
         if (s < n_sets) out[s] = sc;
         __syncwarp();

@@ -29,51 +29,35 @@
 #define PT_FLUSH
 #endif
 
-// ---- cold paths, out of line -------------------------------------------------------------------
-// The per-iteration path of the MH kernel has to stay small: seven warps of an SM walk it at their
-// own pace and share a 32 KB instruction cache (round 1: 276 KB of fully inlined code, 1.7-2.3 stall
-// cycles per issued instruction waiting for fetches, and a CTA-wide re-alignment barrier to contain
-// it).  Everything an iteration only sometimes needs lives in these functions.  They take the
-// launch parameters by reference: the kernels declare them __grid_constant__, so no local copy of
-// the parameter block is made.
-
-template <int K, int WMAX>
-static __device__ __noinline__ int ggm_lane_cold(const PdgParams &P, unsigned short *lidx, int lane, KeyW<WMAX> XK, int k, double *score)
+// work accounting of one evaluated set (pdg_get_work): rare (memo misses only), fire-and-forget
+template <int MODEL>
+__device__ __forceinline__ void account_evaluated(const PdgParams &P, int slot, int k)
 {
-    LaneScratch ls; ls.unused = 0; ls.a = nullptr; ls.idx = lidx;
-    double sc = 0.0;
-    const int e = ggm_lane_score_k<K, WMAX>(P, ls, lane, XK.w, k, sc);
-    *score = sc;
-    return e;
-}
-
-template <int WMAX>
-static __device__ __noinline__ int ggm_set_cold(const PdgParams &P, double *tri32, short *idx, double *big, int lane, KeyW<WMAX> XK, double *score)
-{
-    WarpScratch ws; ws.tri32 = tri32; ws.idx = idx; ws.big = big; ws.kbig = P.kbig;
-    double sc = 0.0;
-    const int e = ggm_set_score<WMAX>(P, ws, XK.w, lane, sc);
-    *score = sc;
-    return e;
-}
-
-template <int WMAX>
-static __device__ __noinline__ void memo_insert_cold(const PdgParams &P, KeyW<WMAX> XK, double val)
-{
-    memo_insert<WMAX>(P.memo, XK.w, P.W, val);
+    const unsigned long long kk = (unsigned long long)k;
+    unsigned long long *w = P.work + (size_t)slot * 16;
+    if (MODEL == PDG_MODEL_GGM) {
+        const unsigned long long dm = (P.dmode == 2 ? 2ull : 1ull);
+        atomicAdd(&w[0], 8ull * kk * kk * dm);
+        atomicAdd(&w[1], (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * dm);
+    } else {
+        atomicAdd(&w[0], (unsigned long long)P.nrows * kk);
+    }
+    atomicAdd(&w[2], 1ull);
+    atomicAdd(&w[3], kk);
 }
 
 // Scores of up to 32 complete sets, one per lane (`need` lanes carry a key each): ONE parallel round
 // trip to the memo table, then
-//   GGM, |X| <= PDG_KT : the lanes that missed factorise their own sets in registers (K = the
-//                        largest missing set of the warp) and publish them
+//   GGM, |X| <= PDG_KT : the lanes that missed factorise their own sets (rolled LDL^T over lane-private
+//                        triangles in the warp's scratch) and publish them
 //   otherwise          : the warp resolves the misses one after the other with the cooperative
 //                        scorers (32-row LDL^T / contingency-table scan)
+// req_sets / req_k: warp-uniform counters of the sets requested (hits + misses) and their sizes.
 // Returns the ERR_* bits raised.
 template <int MODEL, int WMAX, int NB = 4>
 __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch &ws, const LaneScratch &ls, int slot,
                                            int lane, const u64 (&X)[WMAX], bool need, double &score,
-                                           unsigned long long (&wk)[8])
+                                           u32 &req_sets, u32 &req_k)
 {
     const int W = P.W;
     int err = 0;
@@ -82,28 +66,20 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     int kq = 0;
 #pragma unroll
     for (int w = 0; w < WMAX; ++w) kq += __popcll(X[w]);
-    if (need) { wk[4] += 1ull; wk[5] += (unsigned long long)kq; hit = memo_lookup<WMAX>(P.memo, X, W, score); }
+    if (need) hit = memo_lookup<WMAX>(P.memo, X, W, score);
+    req_sets += (u32)__popc(__ballot_sync(PDG_FULL, need));
+    req_k += __reduce_add_sync(PDG_FULL, need ? (u32)kq : 0u);
     u32 miss = __ballot_sync(PDG_FULL, need && !hit);
     if (miss == 0u) return 0;
-    KeyW<WMAX> XK;
-#pragma unroll
-    for (int w = 0; w < WMAX; ++w) XK.w[w] = X[w];
     if (MODEL == PDG_MODEL_GGM) {
         const bool smiss = need && !hit && kq <= PDG_KT;
-        const int kmax = (int)__reduce_max_sync(PDG_FULL, smiss ? (unsigned)kq : 0u);
-        if (kmax > 0) {
+        if (__any_sync(PDG_FULL, smiss)) {
             double s_new = 0.0;
-            const int kk_ = smiss ? kq : 0;
-            if (kmax <= 4 && !PDG_NO_K4) err |= ggm_lane_cold<4, WMAX>(P, ls.idx, lane, XK, kk_, &s_new);
-            else if (kmax <= 8) err |= ggm_lane_cold<8, WMAX>(P, ls.idx, lane, XK, kk_, &s_new);
-            else err |= ggm_lane_cold<12, WMAX>(P, ls.idx, lane, XK, kk_, &s_new);
+            err |= ggm_lane_scores_rolled<WMAX>(P, ws.tri32, ls.idx, lane, X, smiss ? kq : 0, s_new);
             if (smiss) {
                 score = s_new; hit = true;
-                memo_insert_cold<WMAX>(P, XK, s_new);
-                const unsigned long long kk = (unsigned long long)kq, dm = (P.dmode == 2 ? 2ull : 1ull);
-                wk[0] += 8ull * kk * kk * dm;
-                wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * dm;
-                wk[2] += 1ull; wk[3] += kk;
+                memo_insert<WMAX>(P.memo, X, W, s_new);
+                account_evaluated<MODEL>(P, slot, kq);
             }
             __syncwarp();
             miss = __ballot_sync(PDG_FULL, need && !hit);
@@ -118,28 +94,20 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
             src = __ffs((int)__ballot_sync(PDG_FULL, need && !hit && kq == kmax)) - 1;
         }
         u64 Y[WMAX];
-        KeyW<WMAX> YK;
 #pragma unroll
-        for (int w = 0; w < WMAX; ++w) { Y[w] = __shfl_sync(PDG_FULL, X[w], src); YK.w[w] = Y[w]; }
+        for (int w = 0; w < WMAX; ++w) Y[w] = __shfl_sync(PDG_FULL, X[w], src);
         double sc = 0.0;
         int e;
         LlTable tab; tab.cells = 0u; tab.k = 0;
-        if (MODEL == PDG_MODEL_GGM) e = ggm_set_cold<WMAX>(P, ws.tri32, ws.idx, ws.big, lane, YK, &sc);
+        if (MODEL == PDG_MODEL_GGM) e = ggm_set_score<WMAX>(P, ws, Y, lane, sc);
         else e = loglin_set_score<WMAX, NB>(P, ws, slot, Y, lane, sc, tab);
         err |= e;
         if (lane == 0) {
-            if (!e) memo_insert_cold<WMAX>(P, YK, sc);
+            if (!e) memo_insert<WMAX>(P.memo, Y, W, sc);
             int k = 0;
 #pragma unroll
             for (int w = 0; w < WMAX; ++w) k += __popcll(Y[w]);
-            const unsigned long long kk = (unsigned long long)k;
-            if (MODEL == PDG_MODEL_GGM) {
-                wk[0] += 8ull * kk * kk * (P.dmode == 2 ? 2ull : 1ull);
-                wk[1] += (2ull * kk * kk * kk + 3ull * kk * kk + 6ull * kk) * (P.dmode == 2 ? 2ull : 1ull);
-            } else {
-                wk[0] += (unsigned long long)P.nrows * kk;
-            }
-            wk[2] += 1ull; wk[3] += kk;
+            account_evaluated<MODEL>(P, slot, k);
         }
         // every lane waiting for this very key takes the value
         bool same = need && !hit;
@@ -155,11 +123,10 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
                 if (!subs) break;
                 const int zs = __ffs((int)subs) - 1;
                 u64 Zk[WMAX];
-                KeyW<WMAX> ZK;
 #pragma unroll
-                for (int w = 0; w < WMAX; ++w) { Zk[w] = __shfl_sync(PDG_FULL, X[w], zs); ZK.w[w] = Zk[w]; }
+                for (int w = 0; w < WMAX; ++w) Zk[w] = __shfl_sync(PDG_FULL, X[w], zs);
                 const double sz = loglin_subset_score<WMAX>(P, ws, tab, Zk, lane);
-                if (lane == 0) { memo_insert_cold<WMAX>(P, ZK, sz); wk[7] += 1ull; }
+                if (lane == 0) { memo_insert<WMAX>(P.memo, Zk, W, sz); atomicAdd(&P.work[(size_t)slot * 16 + 7], 1ull); }
                 bool sm = need && !hit;
 #pragma unroll
                 for (int w = 0; w < WMAX; ++w) sm = sm && (X[w] == Zk[w]);
@@ -167,33 +134,6 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
             }
         }
         miss = __ballot_sync(PDG_FULL, need && !hit);
-    }
-    return err;
-}
-
-// the rare proposal shapes (parallel_moves.py:138-139, :184-187): an empty subtree connects to one
-// random tree node; a subtree of one or two tree nodes offers one disconnect.  Lane 0 writes the move.
-static __device__ __noinline__ int special_move(const u32 *s_sub32, int nw32, int mtype, int msub, int p, u32 r2, int replay_on,
-                                                int aux, short *s_mvU, short *s_mvUadj)
-{
-    int err = 0;
-    if (mtype == 0) {                         // pm:138-139 one random tree node
-        s_mvU[0] = (short)(replay_on ? aux : (int)__umulhi(r2, (u32)p));
-        s_mvUadj[0] = -1;
-    } else {
-        int a = -1, b = -1;
-        for (int i = 0; i < nw32; ++i) {
-            u32 x = s_sub32[i];
-            while (x) { const int t = i * 32 + __ffs((int)x) - 1; x &= x - 1; if (a < 0) a = t; else if (b < 0) b = t; }
-        }
-        if (msub == 1) { s_mvU[0] = (short)a; s_mvUadj[0] = -1; }          // pm:186-187
-        else {                                  // pm:184-185 one of the two leaves
-            int pick;
-            if (replay_on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) err = ERR_REPLAY; }
-            else pick = (int)(r2 >> 31);
-            s_mvU[0] = (short)(pick ? b : a);
-            s_mvUadj[0] = (short)(pick ? a : b);
-        }
     }
     return err;
 }
@@ -274,21 +214,26 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
     double lbuf = 0.0;                  // logl of iteration (block start + lane): stored 32 at a time, coalesced
     u32 rb0 = 0u, rb1 = 0u, rb2 = 0u, rb3 = 0u;     // Philox draws of iteration (block start + lane)
     int errflag = 0;
-    unsigned long long wk[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    u32 req_sets = 0u, req_k = 0u;      // sets requested / their sizes since the last flush (warp-uniform)
     const u32 lt = (1u << lane) - 1u;
     const int nw32 = (p + 31) >> 5;
     const bool replay_on = DIAG && R.on;
+    // MCMC indices fit 32 bits (pdg_create); the next randomisation is tracked by a counter instead of a
+    // 64-bit modulo per iteration
+    const int it0 = (int)it_begin, it1 = (int)it_end, rz = (int)randomize;
+    int next_rand = rz > 0 ? (int)(((it_begin + rz - 1) / rz) * rz) : 0x7fffffff;
     PT_DECL
 
-    for (long long it = it_begin; it < it_end; ++it) {
-        const int sl = (int)((it - it_begin) & 31);
+    for (int it = it0; it < it1; ++it) {
+        const int sl = (it - it0) & 31;
         // optional re-alignment of the chains of a CTA (PDG_LOCKSTEP; off by default: the loop body
         // now fits the instruction cache and nothing is gained by marching in step)
-        if (lockstep && ((it - it_begin) & (lockstep - 1)) == 0) asm volatile("bar.sync 1, %0;" :: "r"(live_threads) : "memory");
+        if (lockstep && ((it - it0) & (lockstep - 1)) == 0) asm volatile("bar.sync 1, %0;" :: "r"(live_threads) : "memory");
         // ---- junction-tree randomisation every `randomize` iterations (mh_parallel.py:226-228),
         // fused here so that a whole run is ONE launch and no chain ever waits for another.  The
         // randomiser works on the global-memory state and reuses this warp's shared memory.
-        if (randomize > 0 && it % randomize == 0) {
+        if (it == next_rand) {
+            next_rand += rz;
             __syncwarp();
             if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
             __syncwarp();
@@ -418,7 +363,26 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
         if (special) {
             nm = 1;
             if (!replay_on) r2 = __shfl_sync(PDG_FULL, rb2, sl);
-            if (lane == 0) errflag |= special_move(s_sub32, nw32, mtype, msub, p, r2, replay_on ? 1 : 0, aux, s_mvU, s_mvUadj);
+            if (lane == 0) {
+                if (mtype == 0) {                         // pm:138-139 one random tree node
+                    s_mvU[0] = (short)(replay_on ? aux : (int)__umulhi(r2, (u32)p));
+                    s_mvUadj[0] = -1;
+                } else {
+                    int a = -1, b = -1;
+                    for (int i = 0; i < nw32; ++i) {
+                        u32 x = s_sub32[i];
+                        while (x) { const int t = i * 32 + __ffs((int)x) - 1; x &= x - 1; if (a < 0) a = t; else if (b < 0) b = t; }
+                    }
+                    if (msub == 1) { s_mvU[0] = (short)a; s_mvUadj[0] = -1; }          // pm:186-187
+                    else {                                  // pm:184-185 one of the two leaves
+                        int pick;
+                        if (replay_on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) errflag |= ERR_REPLAY; }
+                        else pick = (int)(r2 >> 31);
+                        s_mvU[0] = (short)(pick ? b : a);
+                        s_mvUadj[0] = (short)(pick ? a : b);
+                    }
+                }
+            }
             nfwd = (mtype == 1 && msub == 2) ? 2 : 1;
             if (kind == PDG_KIND_PARALLEL && mtype == 1 && msub == 2) logq = -0.6931471805599453;   // :277
         } else if (kind == PDG_KIND_PARALLEL) {
@@ -490,7 +454,7 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
             double sc = 0.0;
             if (MODEL != PDG_MODEL_UNIFORM) {
                 const int kq = (q == 0) ? kb : (q == 1) ? ks : (q == 2) ? kb + 1 : ks + 1;
-                errflag |= warp_scores<MODEL, WMAX, LIGHT ? 1 : 4>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, wk);
+                errflag |= warp_scores<MODEL, WMAX, LIGHT ? 1 : 4>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, req_sets, req_k);
             }
             PT(4)
             const double sc1 = __shfl_down_sync(PDG_FULL, sc, 1), sc2 = __shfl_down_sync(PDG_FULL, sc, 2),
@@ -568,20 +532,18 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
         k += nm;
         logl_prev = logl_prev + log_p;                      // :304 running sum
         if (lane == sl) lbuf = logl_prev;
-        if (sl == 31 || it + 1 == it_end) {
+        if (sl == 31 || it + 1 == it1) {
             if (lane <= sl) P.logl[(size_t)chain * P.n_samples + (it - sl) + lane] = lbuf;
+            if (lane == 0) {
+                atomicAdd(&P.work[chain * 16 + 4], (unsigned long long)req_sets);
+                atomicAdd(&P.work[chain * 16 + 5], (unsigned long long)req_k);
+            }
+            req_sets = 0u; req_k = 0u;
         }
     }
     __syncwarp();
     PT_FLUSH
     if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
     if (lane == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
-    // work counters are kept per lane: reduce over the warp, one atomic per counter
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        unsigned long long v = wk[q];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PDG_FULL, v, o);
-        if (lane == 0 && v) atomicAdd(&P.work[chain * 16 + q], v);
-    }
     if (errflag) atomicOr(&P.err[chain], errflag);
 }

@@ -10,6 +10,8 @@
 New optional keyword arguments (defaults reproduce the reference's behaviour of one chain):
     n_chains=1   number of independent chains run in one launch; > 1 returns a list of Trajectory
     device=0     CUDA device of this process
+    devices=None list of CUDA devices: the chains are sharded over them (chain c is the same chain
+                 whatever the number of devices)
     chain0=0     global id of the first chain (selects the Philox streams; used for sharding)
     replay=None  a replay log of the reference (oracle/ref_shims.py) to be followed exactly
 
@@ -98,53 +100,104 @@ def _graph_cliques(graph, p):
 def sample_chains(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=1, seed=None,
                   single_move=False, device=0, chain0=0, rec_cap=None, replay=None,
                   want_updates=True, want_logl=True, want_state=True, want_tallies=False, burnin=0,
-                  pooled=False):
-    """Runs n_chains independent chains of the (parallel-moves or single-move) sampler on one GPU."""
+                  pooled=False, devices=None):
+    """Runs n_chains independent chains of the (parallel-moves or single-move) sampler.  One GPU
+    (`device`) by default; `devices=[0, 1, ...]` shards the chains over several GPUs of this process
+    (same chains as a single-GPU run: global chain ids select the random streams) -- the replacement of
+    the reference's process-per-chain wrappers (mh_parallel.py:479-530, :597-650)."""
+    kw = dict(init_graph=init_graph, seed=seed, single_move=single_move, rec_cap=rec_cap, replay=replay,
+              want_updates=want_updates, want_logl=want_logl, want_state=want_state, want_tallies=want_tallies,
+              burnin=burnin, pooled=pooled)
     if seed is None:
-        seed = int(time.time())                          # mh_parallel.py:30,188
-    kind = nat.KIND_SINGLE if single_move else nat.KIND_PARALLEL
+        kw["seed"] = int(time.time())                    # mh_parallel.py:30,188
+    if devices is not None and len(devices) > 1:
+        from paralleldg_b200 import distributed
+        return distributed.sample_chains_multi(n_samples, randomize, sd, sd_graph, devices, n_chains=n_chains,
+                                               chain0=chain0, **kw)
+    if devices is not None and len(devices) == 1:
+        device = devices[0]
+    return sample_chains_end(sample_chains_begin(n_samples, randomize, sd, sd_graph, n_chains=n_chains, device=device,
+                                                 chain0=chain0, **kw))
+
+
+class _Pending(object):
+    """a run that has been enqueued on its device and not yet collected"""
+
+
+def _enqueue(h):
+    h.ctx = engine.make_context(h.sd, h.sd_graph, h.n_chains, h.n_samples, seed=h.seed, chain0=h.chain0,
+                                device=h.device, rec_cap=h.cap, pooled=h.pooled)
+    try:
+        if h.replay is not None:
+            _run_replay(h.ctx, h.kind, h.replay, h.n_chains)
+        else:
+            if h.graph.number_of_edges():
+                h.ctx.set_cliques(_graph_cliques(h.graph, int(h.sd.p)))
+            else:
+                h.ctx.set_cliques(None)
+            h.ctx.randomize(0)
+            h.ctx.sample(h.kind, h.randomize)
+    except Exception:
+        engine.release_context(h.ctx)
+        raise
+
+
+def sample_chains_begin(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=1, seed=None,
+                        single_move=False, device=0, chain0=0, rec_cap=None, replay=None,
+                        want_updates=True, want_logl=True, want_state=True, want_tallies=False, burnin=0,
+                        pooled=False):
+    """Enqueues a run on `device` and returns at once (kernel launches are asynchronous); collect it
+    with sample_chains_end.  Several devices are driven concurrently by calling this once per device."""
+    h = _Pending()
+    h.n_samples, h.randomize, h.sd, h.sd_graph, h.n_chains = int(n_samples), int(randomize), sd, sd_graph, int(n_chains)
+    h.seed = int(time.time()) if seed is None else seed
+    h.kind = nat.KIND_SINGLE if single_move else nat.KIND_PARALLEL
+    h.device, h.chain0, h.replay, h.pooled, h.burnin = device, chain0, replay, pooled, burnin
+    h.want = (want_updates, want_logl, want_state, want_tallies)
     p = int(sd.p)
     if init_graph is not None and len(init_graph):
-        graph = init_graph.copy()
+        h.graph = init_graph.copy()
     else:
-        graph = nx.Graph()
-        graph.add_nodes_from(range(p))
+        h.graph = nx.Graph()
+        h.graph.add_nodes_from(range(p))
     # update records: the parallel-moves sampler can accept several moves per iteration, so the
     # default leaves room for two per iteration; a run that still overflows is repeated (runs are
     # deterministic) with four times the room.  Edge tallies are computed from the records on the
     # device, so they need them there even when the caller does not want them back.
-    keep_records = want_updates or want_tallies
+    h.keep_records = want_updates or want_tallies
     if rec_cap is not None:
-        cap = int(rec_cap)
+        h.cap = int(rec_cap)
     else:
-        cap = max((1 if single_move else 2) * int(n_samples), 64)
-    if not keep_records:
-        cap = 0                                           # recording disabled in the kernel
-    tic = time.time()                                     # (a repeated run counts)
-    for attempt in range(6):
-        ctx = engine.make_context(sd, sd_graph, n_chains, n_samples, seed=seed, chain0=chain0,
-                                  device=device, rec_cap=cap, pooled=pooled)
+        h.cap = max((1 if single_move else 2) * int(n_samples), 64)
+    if not h.keep_records:
+        h.cap = 0                                         # recording disabled in the kernel
+    h.tic = time.time()                                   # (a repeated run counts)
+    h.attempt = 0
+    _enqueue(h)
+    return h
+
+
+def sample_chains_end(h):
+    """Waits for a run started by sample_chains_begin and brings its results to the host."""
+    want_updates, want_logl, want_state, want_tallies = h.want
+    while True:
+        ctx = h.ctx
         try:
-            if replay is not None:
-                _run_replay(ctx, kind, replay, n_chains)
-            else:
-                if graph.number_of_edges():
-                    ctx.set_cliques(_graph_cliques(graph, p))
-                else:
-                    ctx.set_cliques(None)
-                ctx.randomize(0)
-                ctx.sample(kind, randomize)
             try:
                 ctx.sync()
             except nat.NativeError as e:
-                if keep_records and e.code == nat.E_OVERFLOW and attempt < 5:
-                    cap *= 4                              # record capacity exceeded: rerun (deterministic)
+                if h.keep_records and e.code == nat.E_OVERFLOW and h.attempt < 5:
+                    h.cap *= 4                            # record capacity exceeded: rerun (deterministic)
+                    h.attempt += 1
+                    engine.release_context(ctx)
+                    ctx = None
+                    _enqueue(h)
                     continue
                 raise
             toc = time.time()
             out = ChainBatch()
-            out.n_chains, out.n_samples, out.randomize, out.kind = int(n_chains), int(n_samples), int(randomize), kind
-            out.seed, out.chain0, out.sd, out.sd_graph, out.init_graph = seed, chain0, sd, sd_graph, graph
+            out.n_chains, out.n_samples, out.randomize, out.kind = h.n_chains, h.n_samples, h.randomize, h.kind
+            out.seed, out.chain0, out.sd, out.sd_graph, out.init_graph = h.seed, h.chain0, h.sd, h.sd_graph, h.graph
             out.n_proposals, out.n_accepted = ctx.counts()
             out.d2h_bytes += out.n_proposals.nbytes * 2
             if want_logl:
@@ -157,14 +210,14 @@ def sample_chains(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=
                 out.final_edges, out.final_bits = ctx.get_state()
                 out.d2h_bytes += out.final_edges.nbytes + out.final_bits.nbytes
             if want_tallies:
-                out.tallies = ctx.edge_tallies(burnin)
+                out.tallies = ctx.edge_tallies(h.burnin)
                 out.d2h_bytes += out.tallies.nbytes
-            out.time = toc - tic
+            out.time = toc - h.tic
             out.gpu_launches = ctx.launch_count()
             return out
         finally:
-            engine.release_context(ctx)
-    raise nat.NativeError("update-record capacity could not be satisfied")
+            if ctx is not None:
+                engine.release_context(ctx)
 
 
 def _run_replay(ctx, kind, log, n_chains):
@@ -208,7 +261,7 @@ def sample_trajectory(n_samples, randomize, sd, sd_graph, init_graph=None, **arg
     n_chains = int(args.get('n_chains', 1))
     batch = sample_chains(n_samples, randomize, sd, sd_graph, init_graph=init_graph, n_chains=n_chains,
                           seed=args.get('seed', None), single_move=False, device=args.get('device', 0),
-                          chain0=args.get('chain0', 0), replay=args.get('replay', None))
+                          chain0=args.get('chain0', 0), replay=args.get('replay', None), devices=args.get('devices', None))
     return _as_result(batch, n_chains)
 
 
@@ -217,7 +270,7 @@ def sample_trajectory_single_move(n_samples, randomize, sd, sd_graph, init_graph
     n_chains = int(args.get('n_chains', 1))
     batch = sample_chains(n_samples, randomize, sd, sd_graph, init_graph=init_graph, n_chains=n_chains,
                           seed=args.get('seed', None), single_move=True, device=args.get('device', 0),
-                          chain0=args.get('chain0', 0), replay=args.get('replay', None))
+                          chain0=args.get('chain0', 0), replay=args.get('replay', None), devices=args.get('devices', None))
     return _as_result(batch, n_chains)
 
 
@@ -303,7 +356,7 @@ def trajectory_to_file(n_samples, randomize, seqdist, seqdist_graph, output_dire
                        labels=None, **args):
     """mh_parallel.py:391-441; with n_chains > 1 chain c is written to <name>_chain<c>.<ext>"""
     parallel = args.get('parallel', False)
-    passthrough = {k: args[k] for k in ('seed', 'n_chains', 'device', 'chain0') if k in args and args[k] is not None}
+    passthrough = {k: args[k] for k in ('seed', 'n_chains', 'device', 'chain0', 'devices') if k in args and args[k] is not None}
     if parallel:
         res = sample_trajectory(n_samples, randomize, seqdist, seqdist_graph, **passthrough)
     else:

@@ -123,17 +123,22 @@ def _worker(rank, world, port, q):
     tot = int(b.offsets[-1])
     b.records = np.zeros(tot, nat.UPDATE_DTYPE)
     b.records["i"] = np.repeat(np.arange(first, first + count), b.n_accepted)
-    b.bits = np.zeros((tot, 2, 1), np.uint64)
+    b.records["node"] = 7 + rank
+    b.bits = np.full((tot, 2, 1), rank + 1, np.uint64)
+    b.final_edges = np.full((count, 2, 2), rank, np.int32)
+    b.final_bits = np.full((count, 3, 1), rank, np.uint64)
     tallies = np.full((3, 3), rank + 1, np.int64)
     t, nprop, nacc = pd_dist.allreduce_tallies(tallies, b.n_proposals, b.n_accepted)
-    g = pd_dist.gather_batches(b, dst=0)
-    if rank == 0:
-        q.put((t.tolist(), nprop, nacc, g["n_chains"], g["offsets"].tolist(), g["records"]["i"].tolist(),
-               g["n_proposals"].tolist()))
+    g = pd_dist.gather_batches(b)          # sized all_gather_into_tensor: every rank gets everything
+    q.put((rank, t.tolist(), nprop, nacc, g["n_chains"], g["offsets"].tolist(), g["records"]["i"].tolist(),
+           g["n_proposals"].tolist(), g["records"]["node"].tolist(), g["bits"][:, 0, 0].tolist(),
+           g["logl"][:, 0].tolist(), g["final_edges"][:, 0, 0].tolist(), g["chains_per_rank"]))
     dist.destroy_process_group()
 
 
 def test_world_size_2_reduction_and_gather_over_gloo():
+    """the N > 1 path on CPU: all-reduce of tallies / counters and the SIZED tensor gather of ragged
+    per-rank record arrays (no pickling), world size 2 over gloo"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -141,16 +146,20 @@ def test_world_size_2_reduction_and_gather_over_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p_ in procs:
         p_.start()
-    out = q.get(timeout=120)
+    outs = [q.get(timeout=120), q.get(timeout=120)]
     for p_ in procs:
         p_.join(timeout=60)
         assert p_.exitcode == 0
-    t, nprop, nacc, nch, offs, rec_i, props = out
-    assert t == [[3, 3, 3]] * 3
-    assert nprop == sum(range(5)) + 50 and nacc == sum(range(5))
-    assert nch == 5 and props == [10, 11, 12, 13, 14]
-    assert offs == [0, 0, 1, 3, 6, 10]
-    assert rec_i == [1, 2, 2, 3, 3, 3, 4, 4, 4, 4]
+    assert sorted(o[0] for o in outs) == [0, 1]
+    for out in outs:
+        _, t, nprop, nacc, nch, offs, rec_i, props, nodes, bits, logl, fe, per_rank = out
+        assert t == [[3, 3, 3]] * 3
+        assert nprop == sum(range(5)) + 50 and nacc == sum(range(5))
+        assert nch == 5 and props == [10, 11, 12, 13, 14] and per_rank == [3, 2]
+        assert offs == [0, 0, 1, 3, 6, 10]
+        assert rec_i == [1, 2, 2, 3, 3, 3, 4, 4, 4, 4]
+        assert nodes == [7, 7, 7, 8, 8, 8, 8, 8, 8, 8] and bits == [1, 1, 1, 2, 2, 2, 2, 2, 2, 2]
+        assert logl == [0.0, 0.0, 0.0, 1.0, 1.0] and fe == [0, 0, 0, 1, 1]
 
 
 def test_bench_reference_arm_contract():
