@@ -218,6 +218,7 @@ int pdg_destroy(pdg_ctx *ctx)
     if (ctx->d_packed_bits) cudaFree(ctx->d_packed_bits);
     if (ctx->d_sbits) { cudaFree(ctx->d_sbits); cudaFree(ctx->d_sout); }
     if (ctx->d_serr) cudaFree(ctx->d_serr);
+    if (ctx->d_big_list) cudaFree(ctx->d_big_list);
     for (auto *v : {&ctx->ev_run, &ctx->ev_rand, &ctx->ev_free})
         for (auto &e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -40,6 +40,7 @@ struct pdg_ctx {
     unsigned long long *d_tally = nullptr;
     // batch-scorer staging, kept between calls
     u64 *d_sbits = nullptr; double *d_sout = nullptr; int *d_serr = nullptr; long long score_cap = 0;
+    int *d_big_list = nullptr; long long big_cap = 0;     // [0] = count, then the indices of the sets for k_score_big
     // replay staging
     std::vector<void *> replay_tmp;
     // CUDA-event timing of the MH and randomisation launches (events come from a pool and are

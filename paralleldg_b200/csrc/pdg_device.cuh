@@ -50,6 +50,21 @@ __device__ __forceinline__ double draw_unif(u32 k0, u32 k1, u32 chain, u32 iter,
     return u01_from(o[0], o[1]);
 }
 
+// the same draw with the ten rounds unrolled: this one sits on the per-iteration path of the MH
+// kernel (one uniform per proposal), where the loop counter, the key schedule and the register moves
+// of the rolled form are half of its instructions
+__device__ __forceinline__ double draw_unif_unrolled(u32 k0, u32 k1, u32 c0, u32 c1, u32 c2, u32 c3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const u32 n0 = hi1 ^ c1 ^ (k0 + 0x9E3779B9u * (u32)r), n2 = hi0 ^ c3 ^ (k1 + 0xBB67AE85u * (u32)r);
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return u01_from(c0, c1);
+}
+
 // ---- bitsets ---------------------------------------------------------------------------
 __device__ __forceinline__ int bit32(const u32 *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ int bit64(const u64 *w, int i) { return (int)((w[i >> 6] >> (i & 63)) & 1ull); }

@@ -531,25 +531,36 @@ __device__ __forceinline__ int ggm_lane_scores_rolled(const PdgParams &P, double
 #pragma unroll 1
             for (int pass = 0; pass < npass; ++pass) {
                 const double *__restrict__ mat = pass ? P.Dm : P.A;
+                {
+                    double *dst = a;
 #pragma unroll 1
-                for (int i = 0, e = 0; i < k; ++i) {
-                    const double *row = mat + (size_t)idx[i * PDG_SL] * p;
-                    for (int l = 0; l <= i; ++l, ++e) a[e * PDG_SL] = __ldg(row + idx[l * PDG_SL]);
+                    for (int i = 0; i < k; ++i) {
+                        const double *row = mat + (size_t)idx[i * PDG_SL] * p;
+                        const unsigned short *il = idx;
+#pragma unroll 2
+                        for (int l = 0; l <= i; ++l, dst += PDG_SL, il += PDG_SL) *dst = __ldg(row + *il);
+                    }
                 }
                 double prod = 1.0;
+                // (running pointers instead of triangle index arithmetic: dj -> (j, j), rij -> (i, j), clj -> (l, j))
+                double *dj = a;
 #pragma unroll 1
                 for (int j = 0; j < k; ++j) {
-                    const int jj = (j * (j + 1)) >> 1;
-                    const double d = a[(jj + j) * PDG_SL];
+                    const double d = *dj;
                     ok = ok && (d > 0.0);
                     prod *= d;
                     const double inv = 1.0 / d;
+                    double *rij = dj + (j + 1) * PDG_SL;                     // (j + 1, j)
 #pragma unroll 1
                     for (int i = j + 1; i < k; ++i) {
-                        double *ri = a + (((i * (i + 1)) >> 1)) * PDG_SL;
-                        const double f = ri[j * PDG_SL] * inv;
-                        for (int l = j + 1; l <= i; ++l) ri[l * PDG_SL] -= f * a[(((l * (l + 1)) >> 1) + j) * PDG_SL];
+                        const double f = *rij * inv;
+                        double *ril = rij + PDG_SL;                              // (i, j + 1)
+                        const double *clj = dj + (j + 1) * PDG_SL;               // (j + 1, j)
+#pragma unroll 2
+                        for (int l = j + 1; l <= i; ++l) { *ril -= f * *clj; ril += PDG_SL; clj += (l + 1) * PDG_SL; }
+                        rij += (i + 1) * PDG_SL;                                 // (i + 1, j)
                     }
+                    dj += (j + 2) * PDG_SL;                                  // (j + 1, j + 1)
                 }
                 double v;
                 if (prod > 1e-280 && prod < 1e280) v = log(prod);

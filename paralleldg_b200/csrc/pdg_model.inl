@@ -5,6 +5,7 @@
 
 #include "pdg_ctx.h"
 #include "pdg_run.cuh"
+#include "pdg_ggm_big.cuh"
 
 namespace {
 
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
 // above PDG_KT vertices and log-linear sets are resolved cooperatively.  grid <= n_chains because
 // the per-warp scratch (large triangles, cell tables) is sized per chain.
 template <int MODEL, int WMAX>
-__global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err)
+__global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err,
+                                                   int *big_list, int *big_count, int big_kmax)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int W = P.W, lane = threadIdx.x;
@@ -164,11 +166,17 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
         int k = 0;
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) { X[w] = (s < n_sets && w < W) ? bits[(size_t)s * W + w] : 0ull; k += __popcll(X[w]); }
+        // GGM sets above 32 vertices go to the CTA-per-set kernel (pdg_ggm_big.cuh): listed here, scored there
+        bool mine = s < n_sets && k > 0;
+        if (MODEL == PDG_MODEL_GGM && big_list && mine && k >= PDG_BIG_MIN && k <= big_kmax) {
+            big_list[atomicAdd(big_count, 1)] = (int)s;
+            mine = false;
+        }
         double sc = 0.0;
         int e = 0;
-        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, s < n_sets && k > 0, sc, rs, rk);
+        if (MODEL != PDG_MODEL_UNIFORM) e = warp_scores<MODEL, WMAX>(P, ws, ls, slot, lane, X, mine, sc, rs, rk);
         if (e) atomicOr(err, e);
-        if (s < n_sets) out[s] = sc;
+        if (s < n_sets && (mine || k == 0)) out[s] = sc;
         __syncwarp();
     }
 }
@@ -285,9 +293,41 @@ int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_
 #else
     const int sm = tri_bytes_for(ctx->P.ll_cap) + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
 #endif
-    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err);
+    int *d_list = nullptr, *d_count = nullptr;
+    int big_kmax = 0;
+    const int big_bytes = 220 * 1024;
+    if constexpr (MODEL == PDG_MODEL_GGM) {
+        // sets above 32 vertices: listed by the warp kernel, scored one CTA each (TMA-staged rows, blocked LDL^T)
+        if (ctx->P.p >= PDG_BIG_MIN && !getenv("PDG_NO_BIG_KERNEL")) {
+            if (n_sets + 1 > ctx->big_cap) {
+                if (ctx->d_big_list) cudaFree(ctx->d_big_list);
+                ctx->d_big_list = nullptr; ctx->big_cap = 0;
+                CK(cudaMalloc((void **)&ctx->d_big_list, (size_t)(n_sets + 1) * sizeof(int)));
+                ctx->big_cap = n_sets + 1;
+            }
+            d_count = ctx->d_big_list; d_list = ctx->d_big_list + 1;
+            CK(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+            big_kmax = big_smem_layout(ctx->P.p, big_bytes).kmax;
+            if (big_kmax > ctx->P.kbig) big_kmax = ctx->P.kbig;
+        }
+    }
+    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err, d_list, d_count, big_kmax);
     ctx->launches++;
     CK(cudaGetLastError());
+    if constexpr (MODEL == PDG_MODEL_GGM) {
+        if (d_list) {
+            int n_big = 0;
+            CK(cudaMemcpyAsync(&n_big, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (n_big > 0) {
+                CK(cudaFuncSetAttribute(k_score_big<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_bytes));
+                const int g = n_big < ctx->sm_count ? n_big : ctx->sm_count;
+                k_score_big<WMAX><<<g, 256, big_bytes, ctx->stream>>>(ctx->P, d_bits, d_list, n_big, d_out, d_err, big_bytes);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
+        }
+    }
     return PDG_OK;
 }
 

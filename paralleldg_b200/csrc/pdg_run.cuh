@@ -482,9 +482,17 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
                 const double tot = (dl + dp) + logq;
                 double u;
                 if (replay_on) u = R.mv_u[R.it_off[(size_t)chain * (R.n_samples + 1) + it] + j];
-                else u = draw_unif(P.seed_lo, P.seed_hi, gchain, (u32)it, TAG_MOVE, (u32)U);
-                const double e = exp(tot);
-                acc = u <= (e < 1.0 ? e : 1.0);                                                 // :268,:300
+                else u = draw_unif_unrolled(P.seed_lo, P.seed_hi, gchain, (u32)it, TAG_MOVE, (u32)U);
+                // accept iff u <= min(1, exp(tot))  (:268,:300).  A single-precision exp brackets the
+                // threshold to 1e-4 relative (its error stays below 2e-5 wherever it does not underflow,
+                // and where it underflows exp(tot) < 2^-53 <= every non-zero u); only a draw inside the
+                // bracket needs the double-precision exp, so the decision is the exact one.
+                {
+                    const double ef = (double)__expf((float)tot);
+                    if (u <= ef * 0.9999) acc = true;
+                    else if (u > ef * 1.0001) acc = false;
+                    else { const double e = exp(tot); acc = u <= (e < 1.0 ? e : 1.0); }
+                }
                 delta = dl + dp;
                 if (DIAG) {
                     const long long kk = k + j + 1;

@@ -285,3 +285,36 @@ def test_pooled_context_keeps_the_model_and_stays_exact():
     assert not np.array_equal(a.logl, b.logl)
     assert np.array_equal(c.logl, d.logl) and np.array_equal(c.records, d.records)
     assert not np.array_equal(c.logl, b.logl)
+
+
+@pytest.mark.parametrize("p,general_d", [(300, False), (120, True), (71, False)])
+def test_large_cliques_cta_kernel_matches_oracle_and_the_warp_path(monkeypatch, p, general_d):
+    """Sets above 32 vertices go through the CTA-per-set kernel of the batch scorer (rows of A staged by
+    TMA bulk copies, blocked LDL^T in shared memory; pdg_ggm_big.cuh).  Its scores must agree with the
+    oracle's LU log-determinants at 1e-10 and -- because the blocked update keeps the elimination order
+    -- carry the SAME BITS as the warp path (PDG_NO_BIG_KERNEL=1).  p = 71: odd row length, so the staged
+    rows start at 8-byte (not 16-byte) aligned addresses."""
+    from paralleldg_b200 import datagen, engine
+    from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
+    X, _ = datagen.ggm_ar_data(p, 2 * p, seed=p)
+    rng = np.random.RandomState(p)
+    D = np.identity(p)
+    if general_d:
+        B = rng.normal(size=(p, p)) * 0.05
+        D = np.identity(p) + B @ B.T
+    sizes = [s for s in (5, 12, 13, 32, 33, 34, 40, 47, 64, 71, 100, 128, 150, 187, 200, 256, p) if s <= min(p, 256)]
+    sets = [sorted(rng.choice(p, k, replace=False).tolist()) for k in sizes for _ in range(3)]
+    W = (p + 63) // 64
+    bits = _bits(sets, W)
+    m = orc.Model.ggm(X, D, 2.0)
+    want = np.array([m.score(b) for b in bits])
+
+    def run():
+        sd = seqdist.GGMJTPosterior()
+        sd.init_model(X, D, 2.0, {})
+        return engine.scorer_for(sd).ctx.score_sets(bits)
+    got = run()
+    assert close(got, want, 1e-10).all(), np.abs(got - want).max()
+    monkeypatch.setenv("PDG_NO_BIG_KERNEL", "1")
+    warp = run()
+    assert np.array_equal(got, warp), np.abs(got - warp).max()
