@@ -539,7 +539,10 @@ int pdg_sample(pdg_ctx *ctx, int kind, int64_t randomize)
     // a single launch tail per run instead of one per randomisation interval (round 1: a third of every
     // 100-iteration launch was the tail of its slowest CTA).  PDG_FUSED=0 restores one launch per interval
     // with the randomiser as its own kernel in between.
-    bool fused = true;
+    // (the light log-linear kernel -- thousands of short-table chains, two CTAs per SM -- keeps one launch
+    // per interval: 1340 vs 1070 M proposals/s on config 3, its chains are cheap enough for the tail not to
+    // matter and the separate randomiser kernel runs at full occupancy)
+    bool fused = !(ctx->P.model == PDG_MODEL_LOGLIN && ctx->light);
     if (const char *v = getenv("PDG_FUSED")) fused = atoi(v) != 0;
     if (!fused) {
         long long it = 1;

@@ -18,19 +18,21 @@
 #include "pdg_kernels.cuh"
 
 #define PDG_BIG_NB 8            // panel width
-#define PDG_BIG_STAGES 8        // rows in flight per buffer set
+#define PDG_BIG_STAGES 4        // rows in flight per buffer set
 #define PDG_BIG_MIN 33          // smallest set the CTA kernel takes
 #define PDG_BIG_LD 256          // row length of the transposed panel buffer = largest set (PdgParams.kbig <= 256)
 
 struct BigSmem { int off_bar, off_idx, off_red, off_cp, off_stage, off_tri, row_bytes, total, kmax; };
 
+// layout for a given budget of dynamic shared memory: everything but the packed triangle is fixed, the
+// triangle takes the rest (kmax = largest set that fits)
 __host__ __device__ inline BigSmem big_smem_layout(int p, int budget_bytes)
 {
     BigSmem s;
     int o = 0;
     s.off_bar = o;   o += 2 * PDG_BIG_STAGES * 8;
-    s.off_idx = o;   o += 512 * 2;
-    s.off_red = o;   o += 64 * 8;
+    s.off_idx = o;   o += PDG_BIG_LD * 2;
+    s.off_red = o;   o += 8 * 8;
     s.off_cp = o;    o += PDG_BIG_NB * PDG_BIG_LD * 8;             // transposed panel columns [NB][PDG_BIG_LD]
     s.row_bytes = ((p * 8 + 15) / 16) * 16 + 16;                   // one row of A, from a 16-byte-aligned address
     s.off_stage = o; o += 2 * PDG_BIG_STAGES * s.row_bytes;
@@ -41,6 +43,12 @@ __host__ __device__ inline BigSmem big_smem_layout(int p, int budget_bytes)
     s.kmax = k;
     s.total = budget_bytes;
     return s;
+}
+// bytes of dynamic shared memory for sets of at most k vertices
+__host__ inline int big_smem_bytes_for(int p, int k)
+{
+    const BigSmem s = big_smem_layout(p, 0);
+    return s.off_tri + (k * (k + 1) / 2) * 8 + 16;
 }
 
 __device__ __forceinline__ void big_mbar_init(unsigned int bar, int count)

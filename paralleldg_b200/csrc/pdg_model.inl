@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
 // the per-warp scratch (large triangles, cell tables) is sized per chain.
 template <int MODEL, int WMAX>
 __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits, long long n_sets, double *out, int *err,
-                                                   int *big_list, int *big_count, int big_kmax)
+                                                   int *big_list, int *big_count, int big_kmax, int group)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int W = P.W, lane = threadIdx.x;
@@ -160,8 +160,11 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     const int slot = blockIdx.x;
     ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
     u32 rs = 0u, rk = 0u;
-    for (long long s0 = (long long)blockIdx.x * 32; s0 < n_sets; s0 += (long long)gridDim.x * 32) {
-        const long long s = s0 + lane;
+    // `group` sets per warp pass (1 ... 32, lanes 0 ... group - 1): sets that miss the memo and need the whole
+    // warp (contingency-table scans, cliques of 13 ... 32 vertices) are resolved one after the other, so a
+    // batch is spread over as many warps as the launch has before any warp takes a second set
+    for (long long s0 = (long long)blockIdx.x * group; s0 < n_sets; s0 += (long long)gridDim.x * group) {
+        const long long s = (lane < group) ? s0 + lane : n_sets;
         u64 X[WMAX];
         int k = 0;
 #pragma unroll
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
         bool mine = s < n_sets && k > 0;
         if (MODEL == PDG_MODEL_GGM && big_list && mine && k >= PDG_BIG_MIN && k <= big_kmax) {
             big_list[atomicAdd(big_count, 1)] = (int)s;
+            atomicMax(big_count + 1, k);                  // largest listed set: sizes the CTA kernel's shared memory
             mine = false;
         }
         double sc = 0.0;
@@ -208,12 +212,15 @@ int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgRepl
     if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG>, sm))) return rc;
     const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
     pdg_time_begin(ctx, ctx->ev_run);
-    // chains of one CTA can be re-aligned every `lockstep` iterations (power of two); off by default
-    int lockstep = 0;
-    if (wpc > 1) {
-        if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
-        if (lockstep < 0 || (lockstep & (lockstep - 1))) lockstep = 0;
-    }
+    // Chains of one CTA can be re-aligned every `lockstep` iterations (power of two).  Off where the chain
+    // state sits in shared memory (measured: 460 vs 435 M proposals/s at p = 50, 1070 vs 1290 only for the
+    // light log-linear kernel, which runs per-interval launches anyway); on for the large-p kernels, whose
+    // per-iteration path (neighbourhood walk, eight-word keys, in-kernel randomisation over global
+    // memory) is several times longer: in step the warps of an SM share its instruction fetches
+    // (p = 500: 50.5 vs 43.7 M proposals/s).
+    int lockstep = (!SS && MODEL != PDG_MODEL_LOGLIN) ? 16 : 0;
+    if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
+    if (wpc <= 1 || lockstep < 0 || (lockstep & (lockstep - 1))) lockstep = 0;
     k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
     pdg_time_end(ctx, ctx->ev_run);
     ctx->launches++;
@@ -288,6 +295,10 @@ template <int MODEL, int WMAX>
 int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_out, int *d_err)
 {
     long long grid = n_sets < ctx->P.n_chains ? n_sets : ctx->P.n_chains;
+    int group = (int)((n_sets + grid - 1) / grid);
+    group = group < 1 ? 1 : group > 32 ? 32 : group;
+    if (const char *v = getenv("PDG_SCORE_GROUP")) { const int x = atoi(v); if (x >= 1 && x <= 32) group = x; }
+    grid = (n_sets + group - 1) / group < grid ? (n_sets + group - 1) / group : grid;
 #ifdef PDG_LANE_SMEM
     const int sm = PDG_KTRI * 32 * 8 + PDG_KT * 32 * 2 + ((ctx->P.p + 2) * 2 + 15) / 16 * 16;
 #else
@@ -299,30 +310,38 @@ int launch_score_t(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_
     if constexpr (MODEL == PDG_MODEL_GGM) {
         // sets above 32 vertices: listed by the warp kernel, scored one CTA each (TMA-staged rows, blocked LDL^T)
         if (ctx->P.p >= PDG_BIG_MIN && !getenv("PDG_NO_BIG_KERNEL")) {
-            if (n_sets + 1 > ctx->big_cap) {
+            if (n_sets + 2 > ctx->big_cap) {
                 if (ctx->d_big_list) cudaFree(ctx->d_big_list);
                 ctx->d_big_list = nullptr; ctx->big_cap = 0;
-                CK(cudaMalloc((void **)&ctx->d_big_list, (size_t)(n_sets + 1) * sizeof(int)));
-                ctx->big_cap = n_sets + 1;
+                CK(cudaMalloc((void **)&ctx->d_big_list, (size_t)(n_sets + 2) * sizeof(int)));
+                ctx->big_cap = n_sets + 2;
             }
-            d_count = ctx->d_big_list; d_list = ctx->d_big_list + 1;
-            CK(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+            d_count = ctx->d_big_list; d_list = ctx->d_big_list + 2;
+            CK(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), ctx->stream));
             big_kmax = big_smem_layout(ctx->P.p, big_bytes).kmax;
             if (big_kmax > ctx->P.kbig) big_kmax = ctx->P.kbig;
         }
     }
-    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err, d_list, d_count, big_kmax);
+    k_score_sets<MODEL, WMAX><<<(unsigned)grid, 32, sm, ctx->stream>>>(ctx->P, d_bits, n_sets, d_out, d_err, d_list, d_count, big_kmax, group);
     ctx->launches++;
     CK(cudaGetLastError());
     if constexpr (MODEL == PDG_MODEL_GGM) {
         if (d_list) {
-            int n_big = 0;
-            CK(cudaMemcpyAsync(&n_big, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            int hb[2] = {0, 0};
+            CK(cudaMemcpyAsync(hb, d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
+            const int n_big = hb[0];
             if (n_big > 0) {
+                // shared memory for the largest set of THIS batch: sets of <= ~100 vertices leave room for
+                // several CTAs per SM
+                int bytes = big_smem_bytes_for(ctx->P.p, hb[1]);
+                if (bytes > big_bytes) bytes = big_bytes;
                 CK(cudaFuncSetAttribute(k_score_big<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_bytes));
-                const int g = n_big < ctx->sm_count ? n_big : ctx->sm_count;
-                k_score_big<WMAX><<<g, 256, big_bytes, ctx->stream>>>(ctx->P, d_bits, d_list, n_big, d_out, d_err, big_bytes);
+                int per_sm = (227 * 1024) / (bytes + 1024);
+                per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
+                const int cap = ctx->sm_count * per_sm;
+                const int g = n_big < cap ? n_big : cap;
+                k_score_big<WMAX><<<g, 256, bytes, ctx->stream>>>(ctx->P, d_bits, d_list, n_big, d_out, d_err, bytes);
                 ctx->launches++;
                 CK(cudaGetLastError());
             }

@@ -196,12 +196,13 @@ def test_kernel_variants_give_identical_chains(monkeypatch, env):
     test_production_mode_matches_oracle("cfg1_czech_single_s1", 1, 5, 500, 100)
 
 
-def test_loglin_subset_scores_read_off_superset_tables():
+def test_loglin_subset_scores_read_off_superset_tables(monkeypatch):
     """Supersets and their subsets missing together in one 32-set scoring pass: the subsets are marginalised
     out of the superset's count table instead of being scanned -- same bits as the oracle's own counts
     (binary and 3-level data, tables with one and with two packed column groups)."""
     import itertools
     from paralleldg_b200 import engine
+    monkeypatch.setenv("PDG_SCORE_GROUP", "32")       # all 32 sets of a batch in ONE warp pass, as in the sampler
     g = load_golden("scorers")
     rng = np.random.RandomState(7)
     for tag, alpha in (("p15", 1.0), ("l3", 2.0)):
