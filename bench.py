@@ -319,6 +319,7 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
         d2h = 0
         e_props = 0
         batch = None
+        stage_ms = {}
         for s in range(max(min(warmup, 3), 1)):                # untimed warm-up of the same call: pooled
             batch = mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=SEED + s, chain0=chain0,   # context and
                                      device=local_rank, rec_cap=cap, want_tallies=True, pooled=True)  # pinned buffers
@@ -333,6 +334,8 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
                 batch.tallies = t.cpu().numpy()
             e_props += int(batch.n_proposals.sum())
             d2h = batch.d2h_bytes
+            for k_, v_ in batch.timings.items():
+                stage_ms[k_] = stage_ms.get(k_, 0.0) + 1e3 * v_ / steps
         barrier()
         e_s = time.perf_counter() - t0
         et = torch.tensor([e_s], dtype=torch.float64, device="cuda")
@@ -342,6 +345,7 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
             dist.all_reduce(ep, op=dist.ReduceOp.SUM)
         e2e = {"value": float(ep.item()) / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(et.item()) / max(steps, 1),
+               "host_ms_per_stage": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
                "api": "paralleldg_b200.mh_parallel.sample_chains (host numpy in, host numpy out: logl traces, "
                       "compacted update records, final states, edge tallies)"}
         # edge-marginal ESS (second half of the metric), outside the timed region

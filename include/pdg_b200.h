@@ -139,6 +139,14 @@ int pdg_get_logl(pdg_ctx *ctx, void *logl /* double[n_chains][n_samples] */);
  * total = number of records, offsets[n_chains+1] (nullable) */
 int pdg_compact_updates(pdg_ctx *ctx, int64_t *total, void *offsets);
 int pdg_get_updates(pdg_ctx *ctx, void *updates /* pdg_update[total] */, void *bits /* uint64[total][2][W] */);
+/* replaces: the end of sample_trajectory (gtraj.set_logl / set_nupdates / set_jt_updates,
+ * mh_parallel.py:306-311) for all chains in one go: counters, offsets, logl traces (nullable), record
+ * compaction and -- when `tallies` is given -- the edge tallies, with the logl copy on a second stream
+ * overlapping the compaction and tally kernels.  On return `total`, the counters and the offsets are
+ * valid; the logl / tallies copies may still be in flight: the pdg_get_updates call that follows
+ * (buffers sized from `total`) waits for everything. */
+int pdg_collect(pdg_ctx *ctx, int64_t *total, void *n_proposals, void *n_accepted, void *offsets, void *logl,
+                int64_t burnin, void *tallies);
 /* per-proposal diagnostics of the LAST pdg_run (only when enabled): k-indexed, chain-major
  * [n_chains][cap]: dlik, dprior, logq, u (fp64) and acc (int32) */
 int pdg_enable_move_log(pdg_ctx *ctx, int64_t cap_per_chain);

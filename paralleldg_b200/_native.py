@@ -22,7 +22,7 @@ EXPORTS = [
     "pdg_set_cliques", "pdg_randomize", "pdg_init_logl", "pdg_run", "pdg_sample", "pdg_sync",
     "pdg_get_counts", "pdg_get_logl", "pdg_compact_updates", "pdg_get_updates", "pdg_enable_move_log",
     "pdg_get_move_log", "pdg_score_sets", "pdg_edge_tallies", "pdg_launch_count",
-    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed", "pdg_host_alloc", "pdg_host_free", "pdg_probe",
+    "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed", "pdg_host_alloc", "pdg_host_free", "pdg_probe", "pdg_collect",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
         "pdg_host_alloc": (C.c_int, [C.POINTER(vp), i64]),
         "pdg_host_free": (C.c_int, [vp]),
         "pdg_probe": (C.c_int, [i32, i32, C.POINTER(dbl)]),
+        "pdg_collect": (C.c_int, [vp, C.POINTER(i64), vp, vp, vp, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -268,6 +269,24 @@ class Context(object):
         bits = PINNED.empty((tot.value, 2, self.W), np.uint64)
         self._ck(self.L.pdg_get_updates(self.h, _p(rec), _p(bits)))
         return off, rec, bits
+
+    def collect(self, want_logl=True, want_updates=True, want_tallies=False, burnin=0):
+        """everything a finished run returns, with overlapped copies and one wait (pdg_collect):
+        -> dict(n_proposals, n_accepted, offsets, logl, records, bits, tallies)"""
+        tot = C.c_int64(0)
+        out = dict(n_proposals=np.zeros(self.n_chains, np.int64), n_accepted=np.zeros(self.n_chains, np.int64),
+                   offsets=np.zeros(self.n_chains + 1, np.int64), logl=None, records=None, bits=None, tallies=None)
+        if want_logl:
+            out["logl"] = PINNED.empty((self.n_chains, self.n_samples), np.float64)
+        if want_tallies:
+            out["tallies"] = PINNED.empty((self.p, self.p), np.int64)
+        self._ck(self.L.pdg_collect(self.h, C.byref(tot), _p(out["n_proposals"]), _p(out["n_accepted"]), _p(out["offsets"]),
+                                    _p(out["logl"]), int(burnin), _p(out["tallies"])))
+        if want_updates:
+            out["records"] = PINNED.empty((tot.value,), UPDATE_DTYPE)
+            out["bits"] = PINNED.empty((tot.value, 2, self.W), np.uint64)
+        self._ck(self.L.pdg_get_updates(self.h, _p(out["records"]), _p(out["bits"])))
+        return out
 
     def enable_move_log(self, cap):
         self._ck(self.L.pdg_enable_move_log(self.h, int(cap)))

@@ -101,6 +101,29 @@ static int stage(pdg_ctx *ctx, const T *src, size_t count, const T **dst)
     return PDG_OK;
 }
 
+// packed record buffers: grown with headroom and never shrunk -- the total changes a little from run to
+// run, and a cudaFree + cudaMalloc of hundreds of MB per call costs tens of milliseconds
+static int ensure_packed(pdg_ctx *ctx, long long tot)
+{
+    if (tot <= ctx->packed_cap) return PDG_OK;
+    if (ctx->d_packed) { cudaFree(ctx->d_packed); cudaFree(ctx->d_packed_bits); ctx->d_packed = nullptr; ctx->d_packed_bits = nullptr; }
+    ctx->packed_cap = 0;
+    const long long cap = tot + tot / 4 + 1024;
+    CK(cudaMalloc((void **)&ctx->d_packed, (size_t)cap * sizeof(pdg_update)));
+    CK(cudaMalloc((void **)&ctx->d_packed_bits, (size_t)cap * 2 * ctx->P.W * 8));
+    ctx->packed_cap = cap;
+    return PDG_OK;
+}
+
+// tallies are accumulated for a < b only; mirror them
+__global__ void k_symmetrize(unsigned long long *t, int p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p * p) return;
+    const int a = i / p, b = i - a * p;
+    if (a > b) t[i] = t[b * p + a];
+}
+
 extern "C" {
 
 int pdg_abi_version(void) { return PDG_ABI_VERSION; }
@@ -221,7 +244,7 @@ int pdg_destroy(pdg_ctx *ctx)
     if (ctx->d_big_list) cudaFree(ctx->d_big_list);
     for (auto *v : {&ctx->ev_run, &ctx->ev_rand, &ctx->ev_free})
         for (auto &e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy); }
     if (ctx->P.ml_dlik) { cudaFree(ctx->P.ml_dlik); cudaFree(ctx->P.ml_dprior); cudaFree(ctx->P.ml_logq); cudaFree(ctx->P.ml_u); cudaFree(ctx->P.ml_acc); cudaFree(ctx->P.ml_U); }
     delete ctx;
     return PDG_OK;
@@ -609,12 +632,8 @@ int pdg_compact_updates(pdg_ctx *ctx, int64_t *total, void *offsets)
     long long tot = 0;
     CK(cudaMemcpyAsync(&tot, ctx->d_offsets + P.n_chains, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (tot > ctx->packed_cap) {
-        if (ctx->d_packed) { cudaFree(ctx->d_packed); cudaFree(ctx->d_packed_bits); ctx->d_packed = nullptr; ctx->d_packed_bits = nullptr; }
-        CK(cudaMalloc((void **)&ctx->d_packed, (size_t)tot * sizeof(pdg_update)));
-        CK(cudaMalloc((void **)&ctx->d_packed_bits, (size_t)tot * 2 * P.W * 8));
-        ctx->packed_cap = tot;
-    }
+    int rc = ensure_packed(ctx, tot);
+    if (rc) return rc;
     if (tot > 0) {
         k_compact<<<(unsigned)P.n_chains, 128, 0, ctx->stream>>>(P, ctx->d_offsets, ctx->d_packed, ctx->d_packed_bits);
         ctx->launches++;
@@ -627,6 +646,57 @@ int pdg_compact_updates(pdg_ctx *ctx, int64_t *total, void *offsets)
     return PDG_OK;
 }
 
+int pdg_collect(pdg_ctx *ctx, int64_t *total, void *n_proposals, void *n_accepted, void *offsets, void *logl,
+                int64_t burnin, void *tallies)
+{
+    if (!ctx || !total || burnin < 0) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PdgParams &P = ctx->P;
+    const size_t C = (size_t)P.n_chains, pp = (size_t)P.p * P.p;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    }
+    // the log-probability traces leave on the copy stream as soon as the sampling kernels are done,
+    // while this stream scans the record counts, packs the records and tallies the edges
+    CK(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    if (logl) CK(cudaMemcpyAsync(logl, P.logl, C * (size_t)P.n_samples * 8, cudaMemcpyDefault, ctx->copy_stream));
+    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(P.nrec, P.rec_cap, P.n_chains, ctx->d_offsets);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    long long tot = 0;
+    CK(cudaMemcpyAsync(&tot, ctx->d_offsets + P.n_chains, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_proposals) CK(cudaMemcpyAsync(n_proposals, P.kcount, C * 8, cudaMemcpyDefault, ctx->stream));
+    if (n_accepted) CK(cudaMemcpyAsync(n_accepted, P.nrec, C * 8, cudaMemcpyDefault, ctx->stream));
+    if (offsets) CK(cudaMemcpyAsync(offsets, ctx->d_offsets, (C + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));              // (the caller sizes its record buffers from `total`)
+    int rc = ensure_packed(ctx, tot);
+    if (rc) return rc;
+    if (tot > 0) {
+        k_compact<<<(unsigned)P.n_chains, 128, 0, ctx->stream>>>(P, ctx->d_offsets, ctx->d_packed, ctx->d_packed_bits);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->packed_total = tot;
+    *total = tot;
+    if (tallies) {
+        if (!ctx->d_since) {
+            CK(cudaMalloc((void **)&ctx->d_since, C * pp * sizeof(int)));
+            CK(cudaMalloc((void **)&ctx->d_tally, pp * 8));
+        }
+        CK(cudaMemsetAsync(ctx->d_tally, 0, pp * 8, ctx->stream));
+        k_edge_tallies<<<(unsigned)P.n_chains, 32, 0, ctx->stream>>>(P, ctx->d_since, burnin, ctx->d_tally);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        k_symmetrize<<<(unsigned)((pp + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tally, P.p);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(tallies, ctx->d_tally, pp * 8, cudaMemcpyDefault, ctx->stream));
+    }
+    return PDG_OK;                                       // pdg_get_updates / pdg_get_state finish the collection
+}
+
 int pdg_get_updates(pdg_ctx *ctx, void *updates, void *bits)
 {
     if (!ctx) return PDG_E_ARG;
@@ -636,6 +706,7 @@ int pdg_get_updates(pdg_ctx *ctx, void *updates, void *bits)
     if (n && updates) CK(cudaMemcpyAsync(updates, ctx->d_packed, n * sizeof(pdg_update), cudaMemcpyDefault, ctx->stream));
     if (n && bits) CK(cudaMemcpyAsync(bits, ctx->d_packed_bits, n * 2 * ctx->P.W * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));      // a pdg_collect in flight ends here
     return PDG_OK;
 }
 

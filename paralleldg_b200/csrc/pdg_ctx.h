@@ -49,6 +49,7 @@ struct pdg_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_run, ev_rand, ev_free;
     // second stream + events for device-to-host copies that overlap the next launch
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
 };
 
 inline int pdg_fail(pdg_ctx *c, int code, const std::string &msg)

@@ -62,6 +62,7 @@ class ChainBatch(object):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.tallies = None          # int64 [p, p] edge-presence counts summed over chains
+        self.timings = {}            # host seconds per stage of the call (setup_and_run, counts, logl, ...)
 
     def trajectory(self, c):
         t = mcmctraj.Trajectory()
@@ -195,23 +196,34 @@ def sample_chains_end(h):
                     continue
                 raise
             toc = time.time()
+            stamps = [("setup_and_run", toc - h.tic)]
+            last = [toc]
+
+            def lap(name):
+                now = time.time()
+                stamps.append((name, now - last[0]))
+                last[0] = now
             out = ChainBatch()
             out.n_chains, out.n_samples, out.randomize, out.kind = h.n_chains, h.n_samples, h.randomize, h.kind
             out.seed, out.chain0, out.sd, out.sd_graph, out.init_graph = h.seed, h.chain0, h.sd, h.sd_graph, h.graph
-            out.n_proposals, out.n_accepted = ctx.counts()
+            got = ctx.collect(want_logl=want_logl, want_updates=want_updates, want_tallies=want_tallies, burnin=h.burnin)
+            out.n_proposals, out.n_accepted = got["n_proposals"], got["n_accepted"]
             out.d2h_bytes += out.n_proposals.nbytes * 2
             if want_logl:
-                out.logl = ctx.logl()
+                out.logl = got["logl"]
                 out.d2h_bytes += out.logl.nbytes
             if want_updates:
-                out.offsets, out.records, out.bits = ctx.updates()
+                out.offsets, out.records, out.bits = got["offsets"], got["records"], got["bits"]
                 out.d2h_bytes += out.offsets.nbytes + out.records.nbytes + out.bits.nbytes
+            if want_tallies:
+                out.tallies = got["tallies"]
+                out.d2h_bytes += out.tallies.nbytes
+            lap("collect")
             if want_state:
                 out.final_edges, out.final_bits = ctx.get_state()
                 out.d2h_bytes += out.final_edges.nbytes + out.final_bits.nbytes
-            if want_tallies:
-                out.tallies = ctx.edge_tallies(h.burnin)
-                out.d2h_bytes += out.tallies.nbytes
+                lap("state")
+            out.timings = dict(stamps)
             out.time = toc - h.tic
             out.gpu_launches = ctx.launch_count()
             return out
