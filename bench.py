@@ -320,7 +320,8 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
         e_props = 0
         batch = None
         stage_ms = {}
-        for s in range(max(min(warmup, 3), 1)):                # untimed warm-up of the same call: pooled
+        for s in range(max(min(warmup, 3), 2)):                # untimed warm-up of the same call (twice at least: the previous
+                                                               # result stays alive while the next is collected): pooled
             batch = mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=SEED + s, chain0=chain0,   # context and
                                      device=local_rank, rec_cap=cap, want_tallies=True, pooled=True)  # pinned buffers
         barrier()
