@@ -142,6 +142,81 @@ __device__ __forceinline__ RandArgs rand_args(const PdgParams &P)
     return a;
 }
 
+// Maximum cardinality search over the graph adjacency `adj` -> maximal cliques K[0..S), their clique-tree
+// parents and separators (replaces nx.find_cliques + the maximum-weight spanning tree of
+// decomposable.py:124-150: any junction tree is a valid start for the randomisation).  Returns S.
+// key of vertex u = (cardinality << 16) | (0xFFFF - u), 0 once numbered; vertex u = lane + 32 j lives in
+// register j of its lane, so a step is 2 NW max operations, one warp reduction and 2 NW bit tests on the
+// broadcast-loaded adjacency row of the new vertex.  NW = bitset words handled (2: p <= 128, rows in
+// shared memory; 8: rows in global memory, built with L2 atomics, hence read with ld.cg).
+template <int NW, bool ADJ_L2>
+__device__ __forceinline__ int mcs_cliques(const u64 *adj, u64 *K, u64 *sep, u64 *numbered, unsigned short *order,
+                                           unsigned short *cliqueof, short *parent, int p, int W, int lane)
+{
+    constexpr int NJ = 2 * NW;
+    int S = 0, prev_card = 0;
+    u32 key[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { const int u = lane + 32 * j; key[j] = (u < p) ? (u32)(0xFFFFu - u) : 0u; }
+    // (vertex 65535 - u never collides with key 0: u < 512)
+    for (int step = 0; step < p; ++step) {
+        u32 best = 0u;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) best = key[j] > best ? key[j] : best;
+        best = __reduce_max_sync(PDG_FULL, best);
+        const int v = (int)(0xFFFFu - (best & 0xFFFFu)), new_card = (int)(best >> 16);
+        // the row of v, without v itself and split into numbered / not yet numbered neighbours
+        u64 xw[NW], nb[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            xw[w] = (w < W) ? (ADJ_L2 ? __ldcg(&adj[(size_t)v * W + w]) : adj[(size_t)v * W + w]) : 0ull;
+            nb[w] = (w < W) ? numbered[w] : ~0ull;
+            xw[w] &= ~((u64)((v >> 6) == w) << (v & 63));       // (arithmetic: keeps xw[] in registers)
+        }
+        if (new_card <= prev_card) {
+            u32 lastkey = 0u;
+            u64 xl = 0ull;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) xl |= xw[w] & (0ull - (u64)(lane == w));     // this lane's word of the row
+            if (lane < W) {
+                const u64 x0 = xl & numbered[lane];                                  // the separator: numbered neighbours
+                K[(size_t)S * W + lane] = x0; sep[(size_t)S * W + lane] = x0;
+                u64 x = x0;
+                while (x) {
+                    const int b = __ffsll((long long)x) - 1;
+                    x &= x - 1;
+                    const int g = lane * 64 + b;
+                    const u32 k2 = ((u32)order[g] << 16) | (u32)g;
+                    lastkey = k2 > lastkey ? k2 : lastkey;
+                }
+            }
+            lastkey = __reduce_max_sync(PDG_FULL, lastkey);
+            if (lane == 0) parent[S] = (new_card != 0) ? (short)cliqueof[lastkey & 0xFFFFu] : (short)(S == 0 ? -1 : 0);
+            ++S;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            cliqueof[v] = (unsigned short)(S - 1);
+            K[(size_t)(S - 1) * W + (v >> 6)] |= 1ull << (v & 63);
+            order[v] = (unsigned short)step;
+        }
+        // cardinalities of the not yet numbered neighbours, v leaves the candidates
+        const int vslot = (lane == (v & 31)) ? (v >> 5) : 99;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const u64 xu = xw[j >> 1] & ~nb[j >> 1];
+            const u32 inc = (u32)(xu >> (lane + 32 * (j & 1))) & 1u;
+            key[j] += inc << 16;                        // (xu holds unnumbered vertices below p only)
+            key[j] &= 0u - (u32)(vslot != j);           // (arithmetic mask: no dynamic register indexing)
+        }
+        __syncwarp();
+        if (lane == (v >> 6)) numbered[lane] |= 1ull << (v & 63);
+        prev_card = new_card;
+        __syncwarp();
+    }
+    return S;
+}
+
 // randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
 // shared memory.  Works on the global-memory state and rebuilds N and the CSR at the end.
 static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long long chain, u32 iter,
@@ -170,7 +245,7 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
     int *E = P.edges + (size_t)chain * 2 * (p - 1);
     const u32 gchain = P.chain0 + (u32)chain, k0 = P.seed_lo, k1 = P.seed_hi;
 
-    int S = 0, prev_card = 0;
+    int S = 0;
     // Two codings of steps (a) and (b) with identical results: up to 128 vertices the gather /
     // shared-memory form is the shorter one, above it the scatter / register form (1.4 -> 1.0 ms
     // per call at p = 500).
@@ -195,49 +270,7 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
         if (lane < W) { numbered[lane] = 0ull; used[lane] = 0ull; }
         __syncwarp();
 
-        // ---- (b) maximum cardinality search -> cliques K[0..S), parent[], sep[] ----------------
-        for (int step = 0; step < p; ++step) {
-            u32 best = 0u;
-            for (int u = lane; u < p; u += 32)
-                if (!bit64(numbered, u)) { const u32 key = ((u32)card[u] << 16) | (u32)(0xFFFFu - u); best = key > best ? key : best; }
-            best = __reduce_max_sync(PDG_FULL, best);
-            const int v = (int)(0xFFFFu - (best & 0xFFFFu)), new_card = (int)(best >> 16);
-            if (new_card <= prev_card) {
-                u32 lastkey = 0u;
-                if (lane < W) {
-                    const u64 x0 = adj[(size_t)v * W + lane] & numbered[lane];
-                    K[(size_t)S * W + lane] = x0; sep[(size_t)S * W + lane] = x0;
-                    u64 x = x0;
-                    while (x) {
-                        const int b = __ffsll((long long)x) - 1;
-                        x &= x - 1;
-                        const int g = lane * 64 + b;
-                        const u32 key = ((u32)order[g] << 16) | (u32)g;
-                        lastkey = key > lastkey ? key : lastkey;
-                    }
-                }
-                lastkey = __reduce_max_sync(PDG_FULL, lastkey);
-                if (lane == 0) parent[S] = (new_card != 0) ? (short)cliqueof[lastkey & 0xFFFFu] : (short)(S == 0 ? -1 : 0);
-                ++S;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                cliqueof[v] = (unsigned short)(S - 1);
-                K[(size_t)(S - 1) * W + (v >> 6)] |= 1ull << (v & 63);
-                order[v] = (unsigned short)step;
-            }
-            if (lane < W) {
-                u64 x = adj[(size_t)v * W + lane] & ~numbered[lane];
-                if ((v >> 6) == lane) { numbered[lane] |= 1ull << (v & 63); }
-                while (x) {
-                    const int b = __ffsll((long long)x) - 1;
-                    x &= x - 1;
-                    card[lane * 64 + b] += 1;
-                }
-            }
-            prev_card = new_card;
-            __syncwarp();
-        }
+        S = mcs_cliques<2, false>(adj, K, sep, numbered, order, cliqueof, parent, p, W, lane);
 
     } else {
         // ---- (a) graph adjacency: adj[v] = union of the cliques holding v (:201-219; v's own bit is
@@ -266,71 +299,7 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
         __threadfence();          // fire-and-forget reductions: performed before any lane reads a row back
         __syncwarp();
 
-        // ---- (b) maximum cardinality search -> cliques K[0..S), parent[], sep[] ----------------
-        // key of vertex u = (cardinality << 16) | (0xFFFF - u), 0 once numbered; vertex u = lane + 32 j
-        // lives in register j of its lane, so a step is 16 max + one warp reduction, and the
-        // cardinality updates are bit tests on the (broadcast-loaded) adjacency row of the new vertex
-        u32 key[16];
-    #pragma unroll
-        for (int j = 0; j < 16; ++j) { const int u = lane + 32 * j; key[j] = (u < p) ? (u32)(0xFFFFu - u) : 0u; }
-        // (vertex 65535 - u never collides with key 0: u < 512)
-        for (int step = 0; step < p; ++step) {
-            u32 best = 0u;
-    #pragma unroll
-            for (int j = 0; j < 16; ++j) best = key[j] > best ? key[j] : best;
-            best = __reduce_max_sync(PDG_FULL, best);
-            const int v = (int)(0xFFFFu - (best & 0xFFFFu)), new_card = (int)(best >> 16);
-            // the row of v, without v itself and split into numbered / not yet numbered neighbours
-            // (the row was built with atomics in L2: read it there, not through L1)
-            u64 xw[8], nb[8];
-    #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                xw[w] = (w < W) ? __ldcg(&adj[(size_t)v * W + w]) : 0ull;
-                nb[w] = (w < W) ? numbered[w] : ~0ull;
-                xw[w] &= ~((u64)((v >> 6) == w) << (v & 63));       // (arithmetic: keeps xw[] in registers)
-            }
-            if (new_card <= prev_card) {
-                u32 lastkey = 0u;
-                u64 xl = 0ull;
-    #pragma unroll
-                for (int w = 0; w < 8; ++w) xl |= xw[w] & (0ull - (u64)(lane == w));     // this lane's word of the row
-                if (lane < W) {
-                    const u64 x0 = xl & numbered[lane];                                  // the separator: numbered neighbours
-                    K[(size_t)S * W + lane] = x0; sep[(size_t)S * W + lane] = x0;
-                    u64 x = x0;
-                    while (x) {
-                        const int b = __ffsll((long long)x) - 1;
-                        x &= x - 1;
-                        const int g = lane * 64 + b;
-                        const u32 k2 = ((u32)order[g] << 16) | (u32)g;
-                        lastkey = k2 > lastkey ? k2 : lastkey;
-                    }
-                }
-                lastkey = __reduce_max_sync(PDG_FULL, lastkey);
-                if (lane == 0) parent[S] = (new_card != 0) ? (short)cliqueof[lastkey & 0xFFFFu] : (short)(S == 0 ? -1 : 0);
-                ++S;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                cliqueof[v] = (unsigned short)(S - 1);
-                K[(size_t)(S - 1) * W + (v >> 6)] |= 1ull << (v & 63);
-                order[v] = (unsigned short)step;
-            }
-            // cardinalities of the not yet numbered neighbours, v leaves the candidates
-            const int vslot = (lane == (v & 31)) ? (v >> 5) : 99;
-    #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const u64 xu = xw[j >> 1] & ~nb[j >> 1];
-                const u32 inc = (u32)(xu >> (lane + 32 * (j & 1))) & 1u;
-                key[j] += inc << 16;                        // (xu holds unnumbered vertices below p only)
-                key[j] &= 0u - (u32)(vslot != j);           // (arithmetic mask: no dynamic register indexing)
-            }
-            __syncwarp();
-            if (lane == (v >> 6)) numbered[lane] |= 1ull << (v & 63);
-            prev_card = new_card;
-            __syncwarp();
-        }
-
+        S = mcs_cliques<8, true>(adj, K, sep, numbered, order, cliqueof, parent, p, W, lane);
     }
 
     // per clique: which words are non-empty (W <= 8 -> one byte) and the separator size, in shared
