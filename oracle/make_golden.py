@@ -382,6 +382,42 @@ def czech_posterior_fixture(ref):
     save("czech_posterior", **out)
 
 
+def generators_fixture(ref):
+    """Outputs of the reference's own data generators: sample_random_AR_graph
+    (decomposable.py:163-178), g_intra_class.cov_matrix (:53-98), sample_hyper_consistent_parameters
+    (discrete_dec_log_linear.py:108-201) with the clique order it used, and the joint table
+    locals_to_joint_prob_table builds from them (:276-292)."""
+    import networkx as nx
+    rs.postprocess_shims()                      # np.float_ (discrete_dec_log_linear.py:158,161)
+    if not hasattr(nx, "from_numpy_matrix"):
+        nx.from_numpy_matrix = nx.from_numpy_array
+    out = {}
+    for tag, p, seed in (("a", 30, 11), ("b", 64, 12)):
+        np.random.seed(seed)
+        g = ref.dlib.sample_random_AR_graph(p, 5)
+        out["ar_%s_p" % tag] = np.int64(p)
+        out["ar_%s_seed" % tag] = np.int64(seed)
+        out["ar_%s_adj" % tag] = nx.to_numpy_array(g, nodelist=range(p)).astype(np.int8)
+        out["ar_%s_cov" % tag] = np.asarray(ref.gic.cov_matrix(g, 0.9, 1.0), dtype=np.float64)
+    for tag, p, seed, lvl in (("a", 8, 21, [2, 3, 2, 2, 3, 2, 2, 2]), ("b", 12, 22, [2] * 12)):
+        np.random.seed(seed)
+        g = ref.dlib.sample_random_AR_graph(p, 3)
+        levels = np.array([list(range(l)) for l in lvl], dtype=object)
+        jt = ref.dlib.junction_tree(g)
+        C = ref.jtlib.peo(jt)[0]
+        np.random.seed(seed + 100)
+        params = ref.loglin.sample_hyper_consistent_parameters(g, 1.0, levels)
+        out["hc_%s_adj" % tag] = nx.to_numpy_array(g, nodelist=range(p)).astype(np.int8)
+        out["hc_%s_levels" % tag] = np.array(lvl, dtype=np.int64)
+        out["hc_%s_seed" % tag] = np.int64(seed + 100)
+        out["hc_%s_order" % tag] = np.array([rs.set_to_bits(c, 1)[0] for c in C], dtype=np.uint64)
+        for i, c in enumerate(C):
+            out["hc_%s_table_%d" % (tag, i)] = np.asarray(params[c], dtype=np.float64)
+        if p <= 8:
+            out["hc_%s_joint" % tag] = np.asarray(ref.loglin.locals_to_joint_prob_table(g, params, levels), dtype=np.float64)
+    save("generators", **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = rs.load_reference()
@@ -430,6 +466,8 @@ def main():
         from paralleldg_b200 import datagen
         data, lv, adj = datagen.loglin_ar_data(62, 6000, seed=62)
         loglin_case(ref, "loglin62_parallel_s1", data, lv, "parallel", 1500, 100, 1)
+    if want("generators"):
+        generators_fixture(ref)
     if want("czech_posterior"):
         czech_posterior_fixture(ref)
     if want("ggm50"):
