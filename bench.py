@@ -349,19 +349,24 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
                "host_ms_per_stage": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
                "api": "paralleldg_b200.mh_parallel.sample_chains (host numpy in, host numpy out: logl traces, "
                       "compacted update records, final states, edge tallies)"}
-        # edge-marginal ESS (second half of the metric), outside the timed region
+        # edge-marginal ESS (second half of the metric), outside the timed region: every chain, on the
+        # device (pdg_edge_ess), from one more run of the same call
         if do_ess:
             try:
-                from paralleldg_b200 import ess as esslib
-                sample = list(range(0, C, max(1, C // 16)))[:16]
                 burn = M // 5
-                per_chain = esslib.batch_edge_ess(batch.offsets, batch.records, batch.bits, w["p"], M, sample, burnin=burn)
-                per_chain = per_chain[np.isfinite(per_chain)]
+                eb = mh.sample_chains(M, R, sd, sdg, n_chains=C, seed=SEED + 10 + steps - 1, chain0=chain0, device=local_rank,
+                                      rec_cap=cap, want_ess=True, want_logl=False, want_updates=False, want_state=False,
+                                      burnin=burn, pooled=True)
+                per_chain = eb.edge_ess[np.isfinite(eb.edge_ess)]
                 ess_info = {"edge_ess_per_chain_mean": float(per_chain.mean()) if len(per_chain) else None,
-                            "chains_sampled": len(sample), "burnin": burn,
+                            "chains": int(C), "chains_with_a_qualifying_edge": int(len(per_chain)), "burnin": burn,
+                            "post_ms": round(1e3 * eb.timings.get("post", 0.0), 3), "where": "device (pdg_edge_ess), all chains",
                             "definition": "median over edges with marginal in (0.05,0.95) of N/(1+2 sum rho_h), Geyer truncation"}
                 if ess_info["edge_ess_per_chain_mean"]:
-                    ess_info["ess_per_sec"] = ess_info["edge_ess_per_chain_mean"] * C * world / (e2e["ms_per_step"] * 1e-3)
+                    tot = torch.tensor([float(per_chain.sum())], dtype=torch.float64, device="cuda")
+                    if world > 1:
+                        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+                    ess_info["ess_per_sec"] = float(tot.item()) / (e2e["ms_per_step"] * 1e-3)
             except Exception as ex:       # the estimator must never break the timing line
                 ess_info = {"error": repr(ex)}
         batch = None

@@ -159,6 +159,17 @@ int pdg_score_sets(pdg_ctx *ctx, const void *bits, int64_t n_sets, void *scores)
  * tallies[p][p] int64 += sum over chains and MCMC indices >= burnin of the edge indicator */
 int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies);
 
+/* on-device trajectory post-processing for every chain, from the per-chain update records:
+ * sizes[n_chains][n_samples] int32 = number of edges at every list position (trajectory.py:202-211
+ * size(), positions as in trajectory.py:126-152) */
+int pdg_size_series(pdg_ctx *ctx, void *sizes);
+/* edge-marginal effective sample size per chain (BASELINE.json's second metric): over the list
+ * positions >= burnin, for every edge with lo < marginal < hi the indicator series' autocorrelation
+ * r(h) (auxiliary_functions.py:546-550), ESS = n / (-1 + 2 sum of the initial positive pairs
+ * r(2t) + r(2t+1)); ess[n_chains] fp64 = median over those edges (NaN when none), n_edges[n_chains]
+ * int32 (nullable) = how many qualified */
+int pdg_edge_ess(pdg_ctx *ctx, int64_t burnin, double lo, double hi, void *ess, void *n_edges);
+
 /* measurement support (bench.py): CUDA-event timing of every MH-kernel and randomisation launch
  * on the context's stream, and the algorithmic work the MH kernel performed:
  * for the complete sets actually EVALUATED (memo misses): work[0] = bytes (GGM 8 k^2, log-linear

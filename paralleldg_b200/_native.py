@@ -23,6 +23,7 @@ EXPORTS = [
     "pdg_get_counts", "pdg_get_logl", "pdg_compact_updates", "pdg_get_updates", "pdg_enable_move_log",
     "pdg_get_move_log", "pdg_score_sets", "pdg_edge_tallies", "pdg_launch_count",
     "pdg_enable_timing", "pdg_get_timing", "pdg_get_work", "pdg_set_seed", "pdg_host_alloc", "pdg_host_free", "pdg_probe", "pdg_collect",
+    "pdg_size_series", "pdg_edge_ess",
 ]
 
 
@@ -90,6 +91,8 @@ def lib():
         "pdg_host_free": (C.c_int, [vp]),
         "pdg_probe": (C.c_int, [i32, i32, C.POINTER(dbl)]),
         "pdg_collect": (C.c_int, [vp, C.POINTER(i64), vp, vp, vp, vp, i64, vp]),
+        "pdg_size_series": (C.c_int, [vp, vp]),
+        "pdg_edge_ess": (C.c_int, [vp, i64, dbl, dbl, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -310,6 +313,19 @@ class Context(object):
         out = np.zeros((self.p, self.p), np.int64)
         self._ck(self.L.pdg_edge_tallies(self.h, int(burnin), _p(out)))
         return out
+
+    def size_series(self):
+        """number of edges at every list position of every chain (trajectory.py:202-211), int32 [chains, n_samples]"""
+        out = np.empty((self.n_chains, self.n_samples), np.int32)
+        self._ck(self.L.pdg_size_series(self.h, _p(out)))
+        return out
+
+    def edge_ess(self, burnin=0, lo=0.05, hi=0.95):
+        """per-chain median edge-indicator ESS and the number of edges it is taken over"""
+        ess = np.empty(self.n_chains, np.float64)
+        ne = np.empty(self.n_chains, np.int32)
+        self._ck(self.L.pdg_edge_ess(self.h, int(burnin), float(lo), float(hi), _p(ess), _p(ne)))
+        return ess, ne
 
     def enable_timing(self, on=True):
         self._ck(self.L.pdg_enable_timing(self.h, 1 if on else 0))

@@ -12,6 +12,7 @@
 #define PDG_DEFINE_GLOBAL_KERNELS
 #include "pdg_ctx.h"
 #include "pdg_tally.cuh"
+#include "pdg_post.cuh"
 
 __global__ void k_memo_clear(MemoTable T)
 {
@@ -798,6 +799,76 @@ int pdg_edge_tallies(pdg_ctx *ctx, int64_t burnin, void *tallies)
     for (int a = 0; a < P.p; ++a)
         for (int b = a + 1; b < P.p; ++b) h[(size_t)b * P.p + a] = h[(size_t)a * P.p + b];
     CK(cudaMemcpy(tallies, h.data(), pp * 8, cudaMemcpyDefault));
+    return PDG_OK;
+}
+
+// RAII for the temporaries of the post-processing calls
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+}
+
+int pdg_size_series(pdg_ctx *ctx, void *sizes)
+{
+    if (!ctx || !sizes) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PdgParams &P = ctx->P;
+    const size_t bytes = (size_t)P.n_chains * (size_t)P.n_samples * sizeof(int);
+    cudaPointerAttributes at;
+    const bool on_device = cudaPointerGetAttributes(&at, sizes) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    DevBuf tmp;
+    int *dst = (int *)sizes;
+    if (!on_device) { CK(tmp.alloc(bytes)); dst = (int *)tmp.p; }
+    k_size_series<<<(unsigned)P.n_chains, 32, 0, ctx->stream>>>(P, dst);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (!on_device) CK(cudaMemcpyAsync(sizes, dst, bytes, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PDG_OK;
+}
+
+int pdg_edge_ess(pdg_ctx *ctx, int64_t burnin, double lo, double hi, void *ess, void *n_edges)
+{
+    if (!ctx || !ess || burnin < 0 || burnin >= ctx->P.n_samples) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PdgParams &P = ctx->P;
+    const size_t C = (size_t)P.n_chains, pp = (size_t)P.p * P.p;
+    const long long len = P.n_samples - burnin;
+    const int words = (int)((len + 63) / 64);
+    const size_t smem = (size_t)ESS_WARPS * ((size_t)(words + 2) * 8 + (size_t)(words + 1) * 4);
+    if (smem > 200 * 1024) return fail(ctx, PDG_E_ARG, "pdg_edge_ess: series longer than 400 000 positions");
+    if (!ctx->d_since) {
+        CK(cudaMalloc((void **)&ctx->d_since, C * pp * sizeof(int)));
+        CK(cudaMalloc((void **)&ctx->d_tally, pp * 8));
+    }
+    DevBuf slot, nq, bm, vals, out;
+    CK(slot.alloc(C * pp * sizeof(int)));
+    CK(nq.alloc(C * sizeof(int)));
+    CK(out.alloc(C * 8));
+    k_edge_presence<<<(unsigned)C, 32, 0, ctx->stream>>>(P, ctx->d_since, (int *)slot.p, burnin, lo, hi, (int *)nq.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<int> hq(C);
+    CK(cudaMemcpyAsync(hq.data(), nq.p, C * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int qcap = 1;
+    for (size_t c = 0; c < C; ++c) qcap = hq[c] > qcap ? hq[c] : qcap;
+    long long grid = (long long)ctx->sm_count * 2;
+    if (grid > (long long)C) grid = (long long)C;
+    CK(bm.alloc((size_t)grid * qcap * words * 8));
+    CK(vals.alloc((size_t)grid * qcap * 8));
+    CK(cudaFuncSetAttribute(k_edge_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_edge_ess<<<(unsigned)grid, 32 * ESS_WARPS, smem, ctx->stream>>>(P, (const int *)slot.p, (const int *)nq.p, burnin, qcap,
+                                                                     words, (u64 *)bm.p, (double *)vals.p, (double *)out.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ess, out.p, C * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_edges) CK(cudaMemcpy(n_edges, hq.data(), C * sizeof(int), cudaMemcpyDefault));
     return PDG_OK;
 }
 

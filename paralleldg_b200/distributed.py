@@ -108,7 +108,7 @@ def gather_batches(batch, device=None):
         out["offsets"] = np.concatenate([[0], np.cumsum(per_chain)]).astype(np.int64)
     else:
         out["records"] = out["bits"] = out["offsets"] = None
-    for k_ in ("final_edges", "final_bits"):
+    for k_ in ("final_edges", "final_bits", "edge_ess", "edge_ess_edges", "sizes"):
         v = getattr(batch, k_, None)
         out[k_] = all_gather_sized(v, device)[0] if v is not None else None
     return out
@@ -138,6 +138,9 @@ def _merge(batches, mh):
         out.final_bits = np.concatenate([b.final_bits for b in batches])
     if first.tallies is not None:
         out.tallies = np.sum([b.tallies for b in batches], axis=0)
+    for k_ in ("edge_ess", "edge_ess_edges", "sizes"):
+        if getattr(first, k_, None) is not None:
+            setattr(out, k_, np.concatenate([getattr(b, k_) for b in batches]))
     out.time = max(b.time for b in batches)
     out.gpu_launches = sum(b.gpu_launches for b in batches)
     out.d2h_bytes = sum(b.d2h_bytes for b in batches)
@@ -182,7 +185,8 @@ def sample_chains_sharded(n_samples, randomize, sd, sd_graph, n_chains=1, chain0
     out = mh.ChainBatch()
     out.n_chains, out.n_samples, out.randomize, out.kind = g["n_chains"], local.n_samples, local.randomize, local.kind
     out.seed, out.chain0, out.sd, out.sd_graph, out.init_graph = local.seed, chain0, sd, sd_graph, local.init_graph
-    for k_ in ("n_proposals", "n_accepted", "logl", "records", "bits", "offsets", "final_edges", "final_bits"):
+    for k_ in ("n_proposals", "n_accepted", "logl", "records", "bits", "offsets", "final_edges", "final_bits",
+               "edge_ess", "edge_ess_edges", "sizes"):
         setattr(out, k_, g[k_])
     out.tallies, out.time, out.gpu_launches, out.d2h_bytes = local.tallies, local.time, local.gpu_launches, local.d2h_bytes
     return out

@@ -62,6 +62,9 @@ class ChainBatch(object):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.tallies = None          # int64 [p, p] edge-presence counts summed over chains
+        self.edge_ess = None         # float64 [n_chains] median edge-indicator ESS (want_ess=True), NaN = no edge qualifies
+        self.edge_ess_edges = None   # int32 [n_chains] edges the median is taken over
+        self.sizes = None            # int32 [n_chains, n_samples] graph size per list position (want_sizes=True)
         self.timings = {}            # host seconds per stage of the call (setup_and_run, counts, logl, ...)
 
     def trajectory(self, c):
@@ -101,14 +104,14 @@ def _graph_cliques(graph, p):
 def sample_chains(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=1, seed=None,
                   single_move=False, device=0, chain0=0, rec_cap=None, replay=None,
                   want_updates=True, want_logl=True, want_state=True, want_tallies=False, burnin=0,
-                  pooled=False, devices=None):
+                  pooled=False, devices=None, want_ess=False, want_sizes=False):
     """Runs n_chains independent chains of the (parallel-moves or single-move) sampler.  One GPU
     (`device`) by default; `devices=[0, 1, ...]` shards the chains over several GPUs of this process
     (same chains as a single-GPU run: global chain ids select the random streams) -- the replacement of
     the reference's process-per-chain wrappers (mh_parallel.py:479-530, :597-650)."""
     kw = dict(init_graph=init_graph, seed=seed, single_move=single_move, rec_cap=rec_cap, replay=replay,
               want_updates=want_updates, want_logl=want_logl, want_state=want_state, want_tallies=want_tallies,
-              burnin=burnin, pooled=pooled)
+              burnin=burnin, pooled=pooled, want_ess=want_ess, want_sizes=want_sizes)
     if seed is None:
         kw["seed"] = int(time.time())                    # mh_parallel.py:30,188
     if devices is not None and len(devices) > 1:
@@ -146,7 +149,7 @@ def _enqueue(h):
 def sample_chains_begin(n_samples, randomize, sd, sd_graph, init_graph=None, n_chains=1, seed=None,
                         single_move=False, device=0, chain0=0, rec_cap=None, replay=None,
                         want_updates=True, want_logl=True, want_state=True, want_tallies=False, burnin=0,
-                        pooled=False):
+                        pooled=False, want_ess=False, want_sizes=False):
     """Enqueues a run on `device` and returns at once (kernel launches are asynchronous); collect it
     with sample_chains_end.  Several devices are driven concurrently by calling this once per device."""
     h = _Pending()
@@ -155,6 +158,7 @@ def sample_chains_begin(n_samples, randomize, sd, sd_graph, init_graph=None, n_c
     h.kind = nat.KIND_SINGLE if single_move else nat.KIND_PARALLEL
     h.device, h.chain0, h.replay, h.pooled, h.burnin = device, chain0, replay, pooled, burnin
     h.want = (want_updates, want_logl, want_state, want_tallies)
+    h.want_post = (want_ess, want_sizes)
     p = int(sd.p)
     if init_graph is not None and len(init_graph):
         h.graph = init_graph.copy()
@@ -165,7 +169,7 @@ def sample_chains_begin(n_samples, randomize, sd, sd_graph, init_graph=None, n_c
     # default leaves room for two per iteration; a run that still overflows is repeated (runs are
     # deterministic) with four times the room.  Edge tallies are computed from the records on the
     # device, so they need them there even when the caller does not want them back.
-    h.keep_records = want_updates or want_tallies
+    h.keep_records = want_updates or want_tallies or want_ess or want_sizes
     if rec_cap is not None:
         h.cap = int(rec_cap)
     else:
@@ -219,6 +223,15 @@ def sample_chains_end(h):
                 out.tallies = got["tallies"]
                 out.d2h_bytes += out.tallies.nbytes
             lap("collect")
+            # on-device post-processing of every chain (trajectory.py:202-211; ESS of the edge indicators)
+            if h.want_post[0]:
+                out.edge_ess, out.edge_ess_edges = ctx.edge_ess(h.burnin)
+                out.d2h_bytes += out.edge_ess.nbytes + out.edge_ess_edges.nbytes
+            if h.want_post[1]:
+                out.sizes = ctx.size_series()
+                out.d2h_bytes += out.sizes.nbytes
+            if h.want_post[0] or h.want_post[1]:
+                lap("post")
             if want_state:
                 out.final_edges, out.final_bits = ctx.get_state()
                 out.d2h_bytes += out.final_edges.nbytes + out.final_bits.nbytes

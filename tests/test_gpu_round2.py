@@ -318,3 +318,53 @@ def test_large_cliques_cta_kernel_matches_oracle_and_the_warp_path(monkeypatch, 
     monkeypatch.setenv("PDG_NO_BIG_KERNEL", "1")
     warp = run()
     assert np.array_equal(got, warp), np.abs(got - warp).max()
+
+
+def _exact_ess(x):
+    """ess.ess_1d with the autocorrelation sums of auxiliary_functions.py:546-550 taken directly"""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    m = x.mean()
+    c0 = ((x - m) ** 2).sum() / n
+    tau, t = -1.0, 0
+    while 2 * t + 1 < n:
+        g = 0.0
+        for h in (2 * t, 2 * t + 1):
+            g += ((x[:n - h] - m) * (x[h:] - m)).sum() / n / c0
+        if g <= 0.0:
+            break
+        tau += 2.0 * g
+        t += 1
+    return n / max(tau, 1e-12)
+
+
+@pytest.mark.parametrize("p,burnin", [(12, 0), (12, 500), (70, 300)])
+def test_device_size_series_and_edge_ess_match_the_host_derivation(p, burnin):
+    """pdg_size_series / pdg_edge_ess (every chain, on the device, from the update records) against the
+    host derivations that tests/test_reference_outputs.py pins to the reference's own size() and
+    against the reference's autocorrelation estimator summed directly"""
+    from paralleldg_b200 import datagen, ess as esslib, mh_parallel as mh
+    from paralleldg_b200.distributions import sequential_junction_tree_distributions as seqdist
+    X, _ = datagen.ggm_ar_data(p, 80, seed=5)
+    sd = seqdist.GGMJTPosterior()
+    sd.init_model(X, np.identity(p), 1.0, {})
+    M, C = 3000, 9
+    b = mh.sample_chains(M, 100, sd, mh.get_prior(["mbc", 2.0, 4.0]), n_chains=C, seed=11, burnin=burnin,
+                         want_ess=True, want_sizes=True, want_tallies=True)
+    assert b.sizes.shape == (C, M) and b.edge_ess.shape == (C,)
+    init = np.zeros((p, p), np.uint8)
+    for c in range(C):
+        t = b.trajectory(c)
+        assert np.array_equal(b.sizes[c], np.asarray(t.size(0), dtype=np.int64)), c
+        rec, bits = b.records[b.offsets[c]:b.offsets[c + 1]], b.bits[b.offsets[c]:b.offsets[c + 1]]
+        series = esslib.edge_indicator_series(rec, bits, init, M, burnin)
+        qual = {e: s for e, s in series.items() if 0.05 < s.mean() < 0.95}
+        assert b.edge_ess_edges[c] == len(qual), c
+        if not qual:
+            assert np.isnan(b.edge_ess[c])
+            continue
+        vals = [_exact_ess(s) for s in list(qual.values())[:40]] if len(qual) <= 40 else None
+        host_fft = np.median([esslib.ess_1d(s) for s in qual.values()])
+        assert abs(b.edge_ess[c] - host_fft) <= 1e-6 * host_fft, (c, b.edge_ess[c], host_fft)
+        if vals is not None:
+            assert abs(b.edge_ess[c] - np.median(vals)) <= 1e-9 * np.median(vals), (c, b.edge_ess[c], np.median(vals))
