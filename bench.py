@@ -37,6 +37,8 @@ WORKLOADS = {
     "ggm_ar_p500_n1000_M10000_R100_c1024": dict(model="ggm", p=500, n=1000, M=10000, R=100, chains=1024, seed=500, delta=1.0),
     "loglin_ar_p100_n100000_M10000_R100_c1024": dict(model="loglin", p=100, n=100000, M=10000, R=100, chains=1024, seed=100),
     "loglin_ar_p15_n1000_M10000_R100_c4096": dict(model="loglin", p=15, n=1000, M=10000, R=100, chains=4096, seed=15),
+    # shortened run of config 4 for ncu captures (the full run replays too slowly under the profiler)
+    "ggm_ar_p500_n1000_M2000_R100_c1024": dict(model="ggm", p=500, n=1000, M=2000, R=100, chains=1024, seed=500, delta=1.0),
     "ggm_synth_p50_n100_M10000_R100_c1024": dict(model="ggm", p=50, n=100, M=10000, R=100, chains=1024, seed=50, delta=1.0),
 }
 DEFAULT_WORKLOAD = "ggm_ar_p50_n100_M10000_R100_c1024"
@@ -301,6 +303,7 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
                 "sets_requested_per_step": dw["sets_requested"] / max(steps, 1),
                 "memo_hit_rate": 1.0 - dw["sets"] / float(max(dw["sets_requested"], 1)),
                 "sets_hashed_cells_per_step": dw.get("sets_sparse", 0) / max(steps, 1),
+                "sets_derived_per_step": dw.get("sets_derived", 0) / max(steps, 1),
                 "mean_set_size_requested": dw["sum_k_requested"] / float(max(dw["sets_requested"], 1)),
                 "mean_set_size_evaluated": dw["sum_k"] / float(max(dw["sets"], 1)),
                 "note": "latency/issue-bound integer kernel: scores come from the device-wide memo table, "
@@ -362,13 +365,15 @@ def measure(wname, steps, warmup, rank, world, local_rank, do_e2e=True, do_cpu=T
                             "chains": int(C), "chains_with_a_qualifying_edge": int(len(per_chain)), "burnin": burn,
                             "post_ms": round(1e3 * eb.timings.get("post", 0.0), 3), "where": "device (pdg_edge_ess), all chains",
                             "definition": "median over edges with marginal in (0.05,0.95) of N/(1+2 sum rho_h), Geyer truncation"}
-                if ess_info["edge_ess_per_chain_mean"]:
-                    tot = torch.tensor([float(per_chain.sum())], dtype=torch.float64, device="cuda")
-                    if world > 1:
-                        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-                    ess_info["ess_per_sec"] = float(tot.item()) / (e2e["ms_per_step"] * 1e-3)
+                local_sum = float(per_chain.sum())
             except Exception as ex:       # the estimator must never break the timing line
                 ess_info = {"error": repr(ex)}
+                local_sum = 0.0
+            tot = torch.tensor([local_sum], dtype=torch.float64, device="cuda")
+            if world > 1:                 # (every rank takes part, whatever happened above)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            if float(tot.item()) > 0.0:
+                ess_info["ess_per_sec"] = float(tot.item()) / (e2e["ms_per_step"] * 1e-3)
         batch = None
         engine.clear_pool()
 

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdg_b200.so")
+# (PDG_LIB selects a developer build variant, e.g. one made by `python -m paralleldg_b200.build --variant nb2 ...`)
+LIB_PATH = os.environ.get("PDG_LIB") or os.path.join(_HERE, "libpdg_b200.so")
 
 MODEL_UNIFORM, MODEL_GGM, MODEL_LOGLIN = 0, 1, 2
 PRIOR_MBC, PRIOR_EDGEPENALTY, PRIOR_JUMPPENALTY, PRIOR_UNIFORM = 0, 1, 2, 3

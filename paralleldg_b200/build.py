@@ -41,16 +41,19 @@ def _flags():
     return fl
 
 
-def build_native(force=False, verbose=False):
-    if not force and not _stale():
+def build_native(force=False, verbose=False, variant=None, extra=()):
+    """variant: developer build with extra nvcc flags into libpdg_b200_<variant>.so (select it with PDG_LIB)"""
+    if variant is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(OBJ, exist_ok=True)
+    obj_dir = OBJ if variant is None else OBJ + "_" + variant
+    lib = LIB if variant is None else os.path.join(HERE, "libpdg_b200_%s.so" % variant)
+    os.makedirs(obj_dir, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
     def compile_one(s):
-        o = os.path.join(OBJ, s[:-3] + ".o")
-        cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + _flags()
+        o = os.path.join(obj_dir, s[:-3] + ".o")
+        cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + _flags() + list(extra)
         if verbose:
             cmd.append("-Xptxas=-v")
         cmd += ["-c", os.path.join(CSRC, s), "-o", o]
@@ -63,10 +66,13 @@ def build_native(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    subprocess.check_call([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
-    return LIB
+    subprocess.check_call([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", lib] + objs)
+    return lib
 
 
 if __name__ == "__main__":
-    build_native(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_native(force=True, verbose="-v" in sys.argv, variant=sys.argv[i + 1], extra=sys.argv[i + 2:]))
+    else:
+        print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -147,6 +147,9 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     ctx->wpc = n_chains >= 8 ? 8 : (int)n_chains;      // upper bound; the launcher spreads the chains over all SMs
     if (const char *v = getenv("PDG_WPC")) { const int x = atoi(v); if (x >= 1 && x <= 8) { ctx->wpc = x; ctx->wpc_forced = true; } }
     { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) ctx->sm_count = n; }
+    // two warps per chain (speculative pairs) while that still leaves every chain resident at once
+    ctx->spec = n_chains <= (int64_t)ctx->sm_count * 8;
+    if (const char *v = getenv("PDG_SPEC")) { ctx->spec = atoi(v) != 0; ctx->spec_forced = true; }
     // 16M slots (256 MB) for one- and two-word keys: the p = 50 hit rate saturates at 2^23; wider
     // keys come with far more distinct cliques (p = 500: 21M per run), 32M slots = 2.7 GB there
     ctx->memo_bits = (p > 128) ? 25 : 24;
@@ -171,7 +174,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     TRY(dalloc(ctx, &P.kcount, C));
     TRY(dalloc(ctx, &P.nrec, C));
     TRY(dalloc(ctx, &P.err, C));
-    TRY(dalloc(ctx, &P.work, C * 16));
+    TRY(dalloc(ctx, &P.work, 2 * C * 16));              // (two scratch / work slots per chain: one per warp of a pair)
     TRY(dalloc(ctx, &P.G0, C * pw));
     TRY(dalloc(ctx, &P.rec, C * (size_t)rec_cap));
     TRY(dalloc(ctx, &P.rec_bits, C * (size_t)rec_cap * 2 * P.W));
@@ -181,10 +184,10 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     TRY(dalloc(ctx, &ctx->d_offsets, C + 1));
     // scratch for cliques above the 32-row shared-memory triangle
     P.kbig = p + 1 < 256 ? p + 1 : 256;
-    if (P.kbig > 32) TRY(dalloc(ctx, &P.big, C * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2)));
+    if (P.kbig > 32) TRY(dalloc(ctx, &P.big, 2 * C * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2)));
     else { P.kbig = 0; P.big = nullptr; }
     TRY(cudaMemset(P.err, 0, C * sizeof(int)));
-    TRY(cudaMemset(P.work, 0, C * 16 * sizeof(unsigned long long)));
+    TRY(cudaMemset(P.work, 0, 2 * C * 16 * sizeof(unsigned long long)));
     {
         const int W = P.W;
         ctx->wmax = W <= 1 ? 1 : W <= 2 ? 2 : W <= 4 ? 4 : 8;
@@ -369,13 +372,13 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
         CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * 8, &d_k));
         CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * 8, &d_a));
         CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * (size_t)(nrows + 2) * 8, &d_lg));
-        CK(own((size_t)P.n_chains * hist_cells * 4, &d_hist));
+        CK(own((size_t)2 * P.n_chains * hist_cells * 4, &d_hist));
         CK(own((size_t)sp.nsp * 4, &d_lock));
         CK(own((size_t)sp.nsp * hs * 8, &d_hk));
         CK(own((size_t)sp.nsp * hs * 4, &d_hc));
         CK(own((size_t)sp.nsp * (size_t)(nrows + 2) * 4, &d_cc));
         CK(cudaMemsetAsync(d_data, 0, data_bytes, ctx->stream));
-        CK(cudaMemsetAsync(d_hist, 0, (size_t)P.n_chains * hist_cells * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_hist, 0, (size_t)2 * P.n_chains * hist_cells * 4, ctx->stream));
         CK(cudaMemsetAsync(d_lock, 0, (size_t)sp.nsp * 4, ctx->stream));
         CK(cudaMemsetAsync(d_hk, 0, (size_t)sp.nsp * hs * 8, ctx->stream));
         CK(cudaMemsetAsync(d_hc, 0, (size_t)sp.nsp * hs * 4, ctx->stream));
@@ -408,8 +411,9 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     for (;;) {
         const RunSmem L = run_smem_layout(P.p, P.W, ctx->smem_state, tri_bytes_for(P.ll_cap));
         const RandSmem LR = rand_smem_layout(P.p, P.W);
-        const int per_warp = LR.total > L.total ? LR.total : L.total;
-        if ((long long)per_warp * ctx->wpc <= 200 * 1024 || P.ll_cap <= 1024) break;
+        const int run_bytes = L.total * ((ctx->spec && ctx->spec_forced) ? 2 : 1);    // log-linear: pairs only when forced
+        const int per_chain = LR.total > run_bytes ? LR.total : run_bytes;
+        if ((long long)per_chain * pdg_chains_per_cta(ctx, ctx->light) <= 224 * 1024 || P.ll_cap <= 1024) break;
         P.ll_cap >>= 1;
     }
     ctx->model_set = true;
@@ -918,10 +922,10 @@ int pdg_get_work(pdg_ctx *ctx, int64_t work[16])
     if (!ctx || !work) return PDG_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<unsigned long long> h((size_t)ctx->P.n_chains * 16);
+    std::vector<unsigned long long> h((size_t)ctx->P.n_chains * 2 * 16);
     CK(cudaMemcpy(h.data(), ctx->P.work, h.size() * 8, cudaMemcpyDeviceToHost));
     for (int q = 0; q < 16; ++q) work[q] = 0;
-    for (size_t c = 0; c < (size_t)ctx->P.n_chains; ++c) for (int q = 0; q < 16; ++q) work[q] += (int64_t)h[c * 16 + q];
+    for (size_t c = 0; c < (size_t)ctx->P.n_chains * 2; ++c) for (int q = 0; q < 16; ++q) work[q] += (int64_t)h[c * 16 + q];
     return PDG_OK;
 }
 

@@ -30,6 +30,8 @@ struct pdg_ctx {
     int sm_count = 148;
     bool smem_state = false;
     bool light = false;                   // log-linear model with few rows: the 128-register MH kernel
+    bool spec = false;                    // two warps per chain (speculative pairs, pdg_run.cuh): chains <= 8 per SM
+    bool spec_forced = false;             // PDG_SPEC set: use / do not use them whatever the model
     int memo_bits = 24;
     // compaction
     long long *d_offsets = nullptr;
@@ -51,6 +53,17 @@ struct pdg_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy = nullptr;
 };
+
+// chains per CTA of the MH kernel: spread over ALL SMs (1024 chains on 148 SMs -> 7 per CTA, 147 CTAs,
+// instead of 128 CTAs of 8); with more chains than fit at once, whole waves of equal size
+inline int pdg_chains_per_cta(const pdg_ctx *ctx, bool light)
+{
+    if (ctx->wpc_forced) return ctx->wpc;
+    const long long resident = (long long)ctx->sm_count * ((light && !ctx->spec) ? 2 : 1);
+    const long long waves = (ctx->P.n_chains + resident * 8 - 1) / (resident * 8);
+    int wpc = (int)((ctx->P.n_chains + resident * waves - 1) / (resident * waves));
+    return wpc < 1 ? 1 : wpc > 8 ? 8 : wpc;
+}
 
 inline int pdg_fail(pdg_ctx *c, int code, const std::string &msg)
 {

@@ -386,7 +386,7 @@ __device__ __forceinline__ int ggm_lane_score_smem(const PdgParams &P, const Lan
 // 32 KB L1.5 I-cache, several warps per SM at different program counters) and every array in
 // registers.
 #ifdef PDG_PHASE_TIMERS
-__device__ unsigned long long g_pt[8];
+static __device__ unsigned long long g_pt[8];
 #define LPT(i) { const long long n_ = clock64(); lp[i] += (unsigned long long)(n_ - l0); l0 = n_; }
 #else
 #define LPT(i)
@@ -589,7 +589,7 @@ __device__ __forceinline__ void load_row(u64 (&X)[WMAX], const u64 *row, int W)
 // ---- shared-memory layout of one warp of the MH kernel (pdg_run.cuh) --------------------------
 struct RunSmem {
     int off_tri, off_idx, off_sub, off_leaf, off_bnd, off_partner, off_mvU, off_mvUadj, off_csr_off, off_csr_adj,
-        off_M, off_N, off_T, off_lidx, off_tmpU, off_tmpA, off_cnt, total;
+        off_M, off_N, off_T, off_lidx, off_tmpU, off_tmpA, off_cnt, off_pair, total;
 };
 
 __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state, int tri_bytes)
@@ -620,6 +620,7 @@ __host__ __device__ inline RunSmem run_smem_layout(int p, int W, bool smem_state
     s.off_tmpU = o;     o += smem_state ? 0 : a2;      // unsorted boundary of the neighbourhood-driven scan
     s.off_tmpA = o;     o += smem_state ? 0 : a2;
     s.off_cnt = o;      o += 16;
+    s.off_pair = o;     o += 96;                           // two PairBox mailboxes (pdg_run.cuh, SPEC kernels)
     s.total = (o + 15) / 16 * 16;
     return s;
 }

@@ -7,6 +7,8 @@
 // K <= hist_cells (<= 65536), else into a hashed table from a small lock-protected pool.  The lgamma terms
 // come from host-built tables (bit-identical to the reference's math.lgamma) when available.
 #pragma once
+#include <type_traits>
+
 #include "pdg_kernels.cuh"
 
 // Everything the scan needs, by value, so that no address of the kernel parameter block is taken
@@ -20,7 +22,7 @@ struct LoglinArgs {
 };
 template <int WMAX> struct KeyW { u64 w[WMAX]; };
 #ifdef PDG_PHASE_TIMERS
-__device__ unsigned long long g_kh[2][32];      // developer probe: scans and cycles by set size
+static __device__ unsigned long long g_kh[2][32];      // developer probe: scans and cycles by set size
 #endif
 struct ScoreRes { double score; int err; };
 
@@ -86,26 +88,29 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
             unsigned int L4[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) L4[jj] = colinfo[j0 + jj];
-            const bool grpA = j0 < q.slotsA;
+            // (MODE 1: ONE warp-uniform branch per group of four slots -- as a per-statement condition it was
+            // if-converted and both accumulators' multiply-adds were issued for every slot)
+            auto accumulate = [&](auto HSEL) {
+                constexpr int H = decltype(HSEL)::value;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < 4; ++jj) {
 #pragma unroll
-                for (int u = 0; u < NB; ++u) {
-                    const unsigned int w4[4] = {x[jj][u].x, x[jj][u].y, x[jj][u].z, x[jj][u].w};
+                    for (int u = 0; u < NB; ++u) {
+                        const unsigned int w4[4] = {x[jj][u].x, x[jj][u].y, x[jj][u].z, x[jj][u].w};
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        if (MODE == 2) {
-                            c[u][w][0] = c[u][w][0] * L4[jj] + __byte_perm(w4[w], 0u, 0x4240);            // rows 4w, 4w+2
-                            c[u][w][NC - 1] = c[u][w][NC - 1] * L4[jj] + __byte_perm(w4[w], 0u, 0x4341);  // rows 4w+1, 4w+3
-                        } else if (MODE == 1) {
-                            if (grpA) c[u][w][0] = c[u][w][0] * L4[jj] + w4[w];
-                            else c[u][w][NC - 1] = c[u][w][NC - 1] * L4[jj] + w4[w];
-                        } else {
-                            c[u][w][0] = c[u][w][0] * L4[jj] + w4[w];
+                        for (int w = 0; w < 4; ++w) {
+                            if (MODE == 2) {
+                                c[u][w][0] = c[u][w][0] * L4[jj] + __byte_perm(w4[w], 0u, 0x4240);            // rows 4w, 4w+2
+                                c[u][w][NC - 1] = c[u][w][NC - 1] * L4[jj] + __byte_perm(w4[w], 0u, 0x4341);  // rows 4w+1, 4w+3
+                            } else {
+                                c[u][w][H] = c[u][w][H] * L4[jj] + w4[w];
+                            }
                         }
                     }
                 }
-            }
+            };
+            if (MODE == 1 && j0 >= q.slotsA) accumulate(std::integral_constant<int, NC - 1>());
+            else accumulate(std::integral_constant<int, 0>());
             const int nj0 = (j0 + 4 < q.nslots) ? j0 + 4 : 0;
             const long long nbase = nj0 ? base : base + 512 * NB;
             if (nbase < n) issue(nbase, nj0);

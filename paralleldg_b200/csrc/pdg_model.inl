@@ -192,36 +192,41 @@ int set_smem(pdg_ctx *ctx, F f, int bytes)
     return PDG_OK;
 }
 
-template <int MODEL, int WMAX, bool SS, bool LIGHT, bool DIAG>
+#define PDG_SPEC_NO_FIT (-100)
+template <int MODEL, int WMAX, bool SS, bool LIGHT, bool DIAG, bool SPEC>
 int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
     const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
     const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
-    const int per_warp = (randomize > 0 && LR.total > L.total) ? LR.total : L.total;
-    // Chains per CTA: one warp each, spread over ALL SMs (1024 chains on 148 SMs -> 7 warps per CTA, 147
-    // CTAs, instead of 128 CTAs of 8); with more chains than fit at once, whole waves of equal size.
-    int wpc = ctx->wpc;
-    if (!ctx->wpc_forced) {
-        const long long resident = (long long)ctx->sm_count * (LIGHT ? 2 : 1);
-        const long long waves = (ctx->P.n_chains + resident * 8 - 1) / (resident * 8);
-        wpc = (int)((ctx->P.n_chains + resident * waves - 1) / (resident * waves));
-        wpc = wpc < 1 ? 1 : wpc > 8 ? 8 : wpc;
-    }
+    // shared memory per chain: one warp region, or the two regions of a pair back to back; the in-kernel
+    // randomiser may use all of it
+    const int run_bytes = L.total * (SPEC ? 2 : 1);
+    const int per_warp = (randomize > 0 && LR.total > run_bytes) ? LR.total : run_bytes;
+    const int wpc = pdg_chains_per_cta(ctx, LIGHT);          // chains per CTA; SPEC: two warps each
+    const int warps = wpc * (SPEC ? 2 : 1);
     const int sm = per_warp * wpc;
+    if (SPEC && sm > 227 * 1024) return PDG_SPEC_NO_FIT;     // the caller falls back to one warp per chain
     int rc;
-    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG>, sm))) return rc;
+    if ((rc = set_smem(ctx, k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG, SPEC>, sm))) return rc;
     const unsigned grid = (unsigned)((ctx->P.n_chains + wpc - 1) / wpc);
     pdg_time_begin(ctx, ctx->ev_run);
-    // Chains of one CTA can be re-aligned every `lockstep` iterations (power of two).  Off where the chain
-    // state sits in shared memory (measured: 460 vs 435 M proposals/s at p = 50, 1070 vs 1290 only for the
-    // light log-linear kernel, which runs per-interval launches anyway); on for the large-p kernels, whose
-    // per-iteration path (neighbourhood walk, eight-word keys, in-kernel randomisation over global
-    // memory) is several times longer: in step the warps of an SM share its instruction fetches
-    // (p = 500: 50.5 vs 43.7 M proposals/s).
-    int lockstep = (!SS && MODEL != PDG_MODEL_LOGLIN) ? 16 : 0;
+    // Instruction-cache policy.  The kernel is ~14 k instructions; the loop body alone is 28 KB (ncu), the
+    // 32 KB instruction cache is shared by every warp of the SM, and the in-kernel randomiser (run by each
+    // warp every `randomize` iterations) streams another ~90 KB through it.  Two remedies exist: `rsync` --
+    // the chains of a CTA enter every randomisation together (one CTA barrier per interval), so its code
+    // passes through the cache once per interval; `lockstep` -- the chains re-align every N iterations
+    // (power of two >= 2) and share the fetches of the loop body.  Measured (1024 chains, M proposals/s):
+    //   p = 50 GGM, pairs   : neither 465, rsync 526            -> rsync with pairs
+    //   p = 50 GGM, no pairs: neither 495, rsync 483
+    //   p = 500 GGM         : lockstep-16 50.4, neither 43.9, rsync 55.1, both 50.6   -> rsync for large p
+    //   log-linear p = 100  : neither 43.4, rsync 42.2
+    int lockstep = 0;
     if (const char *v = getenv("PDG_LOCKSTEP")) lockstep = atoi(v);
-    if (wpc <= 1 || lockstep < 0 || (lockstep & (lockstep - 1))) lockstep = 0;
-    k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG><<<grid, wpc * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
+    if (wpc <= 1 || lockstep < 2 || (lockstep & (lockstep - 1))) lockstep = 0;
+    int rsync = (SPEC || (!SS && MODEL != PDG_MODEL_LOGLIN)) ? 1 : 0;
+    if (const char *v = getenv("PDG_RSYNC")) rsync = atoi(v);
+    if (rsync && wpc > 1 && randomize > 0) lockstep |= 0x10000;
+    k_mh_run<MODEL, WMAX, SS, LIGHT, DIAG, SPEC><<<grid, warps * 32, sm, ctx->stream>>>(ctx->P, kind, b, e, R, lockstep, ctx->Z, randomize, per_warp);
     pdg_time_end(ctx, ctx->ev_run);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -231,16 +236,28 @@ int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgRepl
 template <int MODEL, int WMAX, bool SS>
 int launch_run_t(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
-    // replay logs and the per-proposal diagnostics go through the DIAG build of the kernel
+    // replay logs and the per-proposal diagnostics go through the DIAG build of the kernel (one warp per chain)
     const bool diag = R.on || ctx->P.mvlog_cap > 0;
+    // Two warps per chain pay where the loop body is small enough for two warps per chain to share the
+    // instruction cache: chain state in shared memory, no table scans (measured, 1024 chains: p = 50 GGM
+    // 495 -> 526 M proposals/s; p = 500 GGM 50 -> 41, log-linear p = 100 43 -> 35).  PDG_SPEC overrides.
+    const bool spec = ctx->spec && (ctx->spec_forced || (SS && MODEL != PDG_MODEL_LOGLIN));
     if constexpr (MODEL == PDG_MODEL_LOGLIN) {
         if (ctx->light) {
-            if (diag) return launch_run_k<MODEL, WMAX, SS, true, true>(ctx, kind, b, e, R, randomize);
-            return launch_run_k<MODEL, WMAX, SS, true, false>(ctx, kind, b, e, R, randomize);
+            if (diag) return launch_run_k<MODEL, WMAX, SS, true, true, false>(ctx, kind, b, e, R, randomize);
+            if (spec) {
+                const int rc = launch_run_k<MODEL, WMAX, SS, true, false, true>(ctx, kind, b, e, R, randomize);
+                if (rc != PDG_SPEC_NO_FIT) return rc;
+            }
+            return launch_run_k<MODEL, WMAX, SS, true, false, false>(ctx, kind, b, e, R, randomize);
         }
     }
-    if (diag) return launch_run_k<MODEL, WMAX, SS, false, true>(ctx, kind, b, e, R, randomize);
-    return launch_run_k<MODEL, WMAX, SS, false, false>(ctx, kind, b, e, R, randomize);
+    if (diag) return launch_run_k<MODEL, WMAX, SS, false, true, false>(ctx, kind, b, e, R, randomize);
+    if (spec) {
+        const int rc = launch_run_k<MODEL, WMAX, SS, false, false, true>(ctx, kind, b, e, R, randomize);
+        if (rc != PDG_SPEC_NO_FIT) return rc;
+    }
+    return launch_run_k<MODEL, WMAX, SS, false, false, false>(ctx, kind, b, e, R, randomize);
 }
 
 // The chain state lives in shared memory whenever p * W * 16 <= 8192 bytes (pdg_create): always for
@@ -363,6 +380,14 @@ int launch_score_m(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_
 
 
 }  // namespace
+
+#if defined(PDG_PHASE_TIMERS) && defined(PDG_TU_IS_LOGLIN)
+// developer probe (PDG_PHASE_TIMERS builds only): scans and cycles by set size, see loglin_scan
+extern "C" int pdg_debug_loglin_kh(unsigned long long *out)
+{
+    return cudaMemcpyFromSymbol(out, g_kh, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 #define PDG_CAT2(a, b) a##b
 #define PDG_CAT(a, b) PDG_CAT2(a, b)

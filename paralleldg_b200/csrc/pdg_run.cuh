@@ -164,19 +164,50 @@ static __device__ __noinline__ void reload_chain_state(const PdgParams &P, unsig
 // so that two CTAs share an SM when a GPU runs more than 1184 chains.
 // DIAG: the variant that can follow a replay log of the reference and keep the per-proposal
 // diagnostics; the production kernels carry neither.
-template <int MODEL, int WMAX, bool SMEM_STATE, bool LIGHT, bool DIAG>
-__global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin,
-                                                long long it_end, const __grid_constant__ PdgReplayDev R, int lockstep,
-                                                RandScratch Z, long long randomize, int smem_per_warp)
+// SPEC: TWO warps per chain.  A chain is one long dependent instruction stream and a GPU that runs
+// 1024 of them has fewer than two warps per scheduler, so the kernel is latency bound.  Iterations
+// that accept nothing leave the state untouched (three out of four at the bench shapes), hence warp 1
+// of a pair works on iteration it + 1 -- enumeration, memo probes, factorisations / table scans,
+// accept decisions, all read-only -- while warp 0 runs iteration it as usual.  When warp 0 accepted
+// nothing, warp 1's iteration is exactly what a sequential run would have computed and it is committed
+// (records, bit flips, counters); otherwise it is discarded and iteration it + 1 is redone from the new
+// state (scores it evaluated stay in the memo table).  Every draw is addressed by (chain, iteration), so
+// the chains are bit-identical to the one-warp kernel's.
+#ifndef PDG_NB
+#define PDG_NB 2          // 512-row blocks per pass of the contingency-table scan (8 loads in flight per lane; 4: 45.3, 2: 47.4 M proposals/s on config 5)
+#endif
+#ifndef PDG_MH_THREADS
+#define PDG_MH_THREADS 256
+#endif
+
+// pair mailbox (shared memory, 64 bytes at RunSmem::off_pair of the pair's first warp)
+struct PairBox {
+    double a_logp, b_logp;
+    int a_nm, a_nacc, b_nm, b_nacc, b_ok, pad;
+};
+
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+
+template <int MODEL, int WMAX, bool SMEM_STATE, bool LIGHT, bool DIAG, bool SPEC>
+__global__ void __launch_bounds__(SPEC ? 512 : PDG_MH_THREADS, (LIGHT && !SPEC) ? 2 : 1)
+k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin, long long it_end,
+         const __grid_constant__ PdgReplayDev R, int lockstep, RandScratch Z, long long randomize, int smem_per_warp)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
     const int p = P.p, W = P.W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const long long chain = (long long)blockIdx.x * wpc + warp;
-    if (chain >= P.n_chains) return;                       // (the optional re-alignment barrier counts live warps only)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = SPEC ? (warp & 1) : 0;                 // 1 = the speculating warp of a pair
+    const int cw = SPEC ? (warp >> 1) : warp;               // chain of this CTA
+    const int wpc = SPEC ? (int)(blockDim.x >> 6) : (int)(blockDim.x >> 5);
+    const long long chain = (long long)blockIdx.x * wpc + cw;
+    if (chain >= P.n_chains) return;                       // (whole pairs leave; the barriers count live warps only)
     const int live_threads = 32 * (int)(((long long)(blockIdx.x + 1) * wpc <= P.n_chains) ? wpc : (P.n_chains - (long long)blockIdx.x * wpc));
     const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
-    unsigned char *smem = smem_all + (size_t)warp * smem_per_warp;
+    // `smem_per_warp` bytes per CHAIN: one warp region (L.total, or the randomiser's layout if larger), or
+    // the two regions of a pair back to back (the randomiser, run by the first warp while the second one
+    // waits, may spread over both).  Chain state and pair mailbox sit in the first warp's region.
+    unsigned char *smem_c = smem_all + (size_t)cw * smem_per_warp;
+    unsigned char *smem = smem_c + (SPEC ? role * L.total : 0);
     u64 *s_sub = (u64 *)(smem + L.off_sub);
     u32 *s_sub32 = (u32 *)(smem + L.off_sub);
     u32 *s_leaf = (u32 *)(smem + L.off_leaf);
@@ -184,15 +215,17 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
     short *s_partner = (short *)(smem + L.off_partner);
     short *s_mvU = (short *)(smem + L.off_mvU);
     short *s_mvUadj = (short *)(smem + L.off_mvUadj);
-    unsigned short *s_off = (unsigned short *)(smem + L.off_csr_off);
-    unsigned short *s_adj = (unsigned short *)(smem + L.off_csr_adj);
+    unsigned short *s_off = (unsigned short *)(smem_c + L.off_csr_off);
+    unsigned short *s_adj = (unsigned short *)(smem_c + L.off_csr_adj);
     short *s_tmpU = (short *)(smem + L.off_tmpU), *s_tmpA = (short *)(smem + L.off_tmpA);
     int *s_cnt = (int *)(smem + L.off_cnt);
+    volatile PairBox *box = (volatile PairBox *)(smem_c + L.off_pair);
+    const int bar_id = 1 + cw;
     WarpScratch ws;
     ws.tri32 = (double *)(smem + L.off_tri);
     ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;
-    const int slot = (int)chain;                           // scratch slot of this warp
+    const int slot = SPEC ? (int)(2 * chain + role) : (int)chain;      // scratch slot of this warp (2 per chain exist)
     ws.big = P.big ? P.big + (size_t)slot * ((size_t)(P.kbig + 1) * (P.kbig + 2) / 2) : nullptr;
     LaneScratch ls;
     ls.unused = 0;
@@ -201,11 +234,12 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
 
     u64 *Mg = P.M + (size_t)chain * p * W;
     u64 *Ng = P.N + (size_t)chain * p * W;
-    u64 *Mc = SMEM_STATE ? (u64 *)(smem + L.off_M) : Mg;
-    u64 *Nc = SMEM_STATE ? (u64 *)(smem + L.off_N) : Ng;
-    u64 *Tt = (u64 *)(smem + L.off_T);                      // only with SMEM_STATE
+    u64 *Mc = SMEM_STATE ? (u64 *)(smem_c + L.off_M) : Mg;
+    u64 *Nc = SMEM_STATE ? (u64 *)(smem_c + L.off_N) : Ng;
+    u64 *Tt = (u64 *)(smem_c + L.off_T);                    // only with SMEM_STATE
 
-    reload_chain_state<SMEM_STATE>(P, smem, chain, lane);
+    if (role == 0) reload_chain_state<SMEM_STATE>(P, smem, chain, lane);
+    if (SPEC) pair_bar(bar_id);
 
     const u32 gchain = P.chain0 + (u32)chain;
     long long k = P.kcount[chain];
@@ -213,8 +247,9 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
     double logl_prev = P.logl[(size_t)chain * P.n_samples + it_begin - 1];
     double lbuf = 0.0;                  // logl of iteration (block start + lane): stored 32 at a time, coalesced
     u32 rb0 = 0u, rb1 = 0u, rb2 = 0u, rb3 = 0u;     // Philox draws of iteration (block start + lane)
+    int rb_blk = -1;                    // which block of 32 iterations the draws belong to
     int errflag = 0;
-    u32 req_sets = 0u, req_k = 0u;      // sets requested / their sizes since the last flush (warp-uniform)
+    u32 req_sets = 0u, req_k = 0u;      // sets requested / their sizes, committed iterations (warp-uniform)
     const u32 lt = (1u << lane) - 1u;
     const int nw32 = (p + 31) >> 5;
     const bool replay_on = DIAG && R.on;
@@ -224,35 +259,102 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
     int next_rand = rz > 0 ? (int)(((it_begin + rz - 1) / rz) * rz) : 0x7fffffff;
     PT_DECL
 
-    for (int it = it0; it < it1; ++it) {
-        const int sl = (it - it0) & 31;
-        // optional re-alignment of the chains of a CTA (PDG_LOCKSTEP; off by default: the loop body
-        // now fits the instruction cache and nothing is gained by marching in step)
-        if (lockstep && ((it - it0) & (lockstep - 1)) == 0) asm volatile("bar.sync 1, %0;" :: "r"(live_threads) : "memory");
+    // stores the running log-probability of iteration x (called for every iteration, in order)
+    auto emit_logl = [&](int x, double v) {
+        const int s = (x - it0) & 31;
+        if (lane == s) lbuf = v;
+        if ((s == 31 || x + 1 == it1) && role == 0 && lane <= s) P.logl[(size_t)chain * P.n_samples + (x - s) + lane] = lbuf;
+    };
+    // accepted proposals in order: record append, bit flips (junction_tree.py:78-100 connect / disconnect)
+    auto apply_accepts = [&](u32 am, bool acc, int itx, long long kbase, int j, int node, int mtype, int U, int Ua,
+                             const u64 (&Cw)[WMAX], const u64 (&Aw)[WMAX]) {
+        if (acc) {
+            const long long slot_r = nrec + __popc(am & lt);
+            if (slot_r < P.rec_cap) {
+                const size_t ro = (size_t)chain * P.rec_cap + slot_r;
+                pdg_update h;
+                h.i = itx; h.k = (int)(kbase + j + 1); h.node = (unsigned short)node; h.U = (unsigned short)U;
+                h.Uadj = (short)Ua; h.type = (unsigned char)mtype; h.pad = 0;
+                P.rec[ro] = h;
+#pragma unroll
+                for (int w = 0; w < WMAX; ++w) if (w < W) { P.rec_bits[ro * 2 * W + w] = Cw[w]; P.rec_bits[ro * 2 * W + W + w] = Aw[w]; }
+            } else if (P.rec_cap > 0) errflag |= ERR_OVERFLOW;      // rec_cap == 0: recording is off
+            if (kbase + j + 1 > 2147483647LL) errflag |= ERR_OVERFLOW;     // pdg_update.k is 32 bits wide
+        }
+        nrec += __popc(am);
+        __syncwarp();
+        if (acc) {
+            atomicXor(&Mc[(size_t)U * W + (node >> 6)], 1ull << (node & 63));
+            atomicXor(&Nc[(size_t)node * W + (U >> 6)], 1ull << (U & 63));
+        }
+        if (!SMEM_STATE) __threadfence();           // the bit flips are performed before any lane reads the rows again
+        __syncwarp();
+    };
+
+    // bit 16 of `lockstep`: the chains of a CTA enter every randomisation together (one CTA barrier per
+    // interval), so that the randomiser's code streams through the instruction cache once per interval
+    // instead of evicting the loop body whenever any one warp of the SM randomises
+    const bool rsync = (lockstep & 0x10000) != 0;
+    lockstep &= 0xffff;
+    int it = it0;
+    int round = 0, lock_epoch = -1;
+    while (it < it1) {
+        // optional re-alignment of the chains of a CTA every `lockstep` iterations (PDG_LOCKSTEP, a power of
+        // two >= 2; on for the large-p kernels, whose per-iteration path does not fit the instruction cache:
+        // in step the warps share its fetches).  A pair advances by one or two iterations per round, so the
+        // barrier is tied to the epoch (it - it0) / lockstep, which every warp enters exactly once.
+        if (lockstep) {
+            const int ep = (it - it0) / lockstep;
+            if (ep != lock_epoch) { lock_epoch = ep; asm volatile("bar.sync 15, %0;" :: "r"((SPEC ? 2 : 1) * live_threads) : "memory"); }
+        }
+        ++round;
+        const long long nrec_round = nrec;
         // ---- junction-tree randomisation every `randomize` iterations (mh_parallel.py:226-228),
         // fused here so that a whole run is ONE launch and no chain ever waits for another.  The
         // randomiser works on the global-memory state and reuses this warp's shared memory.
         if (it == next_rand) {
             next_rand += rz;
-            __syncwarp();
-            if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
-            __syncwarp();
-            if (!SMEM_STATE) __threadfence();       // rows flipped with L2 atomics: nothing stale in L1 for the randomiser's loads
-            randomize_chain(rand_args(P), Z, chain, (u32)it, smem, lane);
-            __syncwarp();
-            reload_chain_state<SMEM_STATE>(P, smem, chain, lane);
+            if (rsync) asm volatile("bar.sync 14, %0;" :: "r"((SPEC ? 2 : 1) * live_threads) : "memory");
+            if (role == 0) {
+                __syncwarp();
+                if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
+                __syncwarp();
+                if (!SMEM_STATE) __threadfence();       // rows flipped with L2 atomics: nothing stale in L1 for the randomiser's loads
+                randomize_chain(rand_args(P), Z, chain, (u32)it, smem, lane);
+                __syncwarp();
+                reload_chain_state<SMEM_STATE>(P, smem, chain, lane);
+            }
+            if (SPEC) pair_bar(bar_id);
         }
+        const int my = it + role;          // the iteration this warp works on
+        // warp 1 sits a round out when its iteration does not exist or starts with a randomisation
+        const bool active = role == 0 || (my < it1 && my != next_rand);
+        // results of this warp's iteration
+        int nm = 0, node = 0, mtype = 0;
+        double log_p = 0.0;
+        bool spec_ok = true;
+        u32 it_req_sets = 0u, it_req_k = 0u;
+        int it_err = 0;
+        // warp 1: the accept decisions of its (single) scoring pass, applied only on commit
+        u32 pend_am = 0u; bool pend_acc = false; int pend_U = 0, pend_Ua = -1, pend_j = 0;
+        u64 pend_C[WMAX], pend_A[WMAX];
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) { pend_C[w] = 0ull; pend_A[w] = 0ull; }
+        if (active) {
         // ---- draws (mh_parallel.py:230-231): one Philox block per iteration, 32 iterations at a time
-        // (lane l draws for iteration it + l), handed out by shuffle
-        int node, mtype, aux = -1;
+        // (lane l draws for iteration block start + l), handed out by shuffle
+        const int sl = (my - it0) & 31;
+        int aux = -1;
         u32 r2 = 0u, r3 = 0u;
         if (replay_on) {
-            const size_t o = (size_t)chain * R.n_samples + it;
+            const size_t o = (size_t)chain * R.n_samples + my;
             node = R.it_node[o]; mtype = R.it_mtype[o]; aux = R.it_aux[o];
         } else {
-            if (sl == 0) {
+            const int blk = (my - it0) >> 5;
+            if (blk != rb_blk) {
+                rb_blk = blk;
                 u32 r[4];
-                philox4x32_10(gchain, (u32)(it + lane), TAG_ITER, 0u, P.seed_lo, P.seed_hi, r);
+                philox4x32_10(gchain, (u32)(my - sl + lane), TAG_ITER, 0u, P.seed_lo, P.seed_hi, r);
                 rb0 = r[0]; rb1 = r[1]; rb2 = r[2]; rb3 = r[3];
             }
             node = (int)__umulhi(__shfl_sync(PDG_FULL, rb0, sl), (u32)p);
@@ -270,7 +372,7 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
         const bool special = (mtype == 0 && msub == 0) || (mtype == 1 && msub <= 2);
         // ---- one pass over the tree: leaves of the induced subtree / its outer boundary ------
         // (parallel_moves.py:193-208 and :253-272); proposals come out in ascending tree-node order
-        int nm = 0, nleaf = 0, nbnd = 0;
+        int nleaf = 0, nbnd = 0;
         if (!SMEM_STATE) {
             // Large p (state in global memory): neighbourhood-driven enumeration.  List the few tree
             // nodes of the subtree, walk only THEIR adjacency lists (leaves: exactly one neighbour
@@ -376,7 +478,7 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
                     if (msub == 1) { s_mvU[0] = (short)a; s_mvUadj[0] = -1; }          // pm:186-187
                     else {                                  // pm:184-185 one of the two leaves
                         int pick;
-                        if (replay_on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) errflag |= ERR_REPLAY; }
+                        if (replay_on) { pick = (aux == a) ? 0 : 1; if (aux != a && aux != b) it_err |= ERR_REPLAY; }
                         else pick = (int)(r2 >> 31);
                         s_mvU[0] = (short)(pick ? b : a);
                         s_mvUadj[0] = (short)(pick ? a : b);
@@ -388,13 +490,13 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
         } else if (kind == PDG_KIND_PARALLEL) {
             if (replay_on) {
                 // the reference's ORDER (python set iteration); the SET is checked against ours
-                const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
-                const long long cnt = R.it_off[(size_t)chain * (R.n_samples + 1) + it + 1] - o;
-                if (cnt != nm) { errflag |= ERR_REPLAY; nm = (int)(cnt < nm ? cnt : nm); }
+                const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + my];
+                const long long cnt = R.it_off[(size_t)chain * (R.n_samples + 1) + my + 1] - o;
+                if (cnt != nm) { it_err |= ERR_REPLAY; nm = (int)(cnt < nm ? cnt : nm); }
                 __syncwarp();
                 for (int j = lane; j < nm; j += 32) {
                     const int U = R.mv_U[o + j], Ua = R.mv_Uadj[o + j];
-                    if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
+                    if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) it_err |= ERR_REPLAY;
                     s_mvU[j] = (short)U; s_mvUadj[j] = (short)Ua;
                 }
             }
@@ -402,9 +504,9 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
             // single move: moves[0] after np.random.shuffle (:87,:95 / :128,:138)
             int U, Ua;
             if (replay_on) {
-                const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + it];
+                const long long o = R.it_off[(size_t)chain * (R.n_samples + 1) + my];
                 U = R.mv_U[o]; Ua = R.mv_Uadj[o];
-                if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) errflag |= ERR_REPLAY;
+                if (U < 0 || U >= p || !bit32(set, U) || s_partner[U] != Ua) it_err |= ERR_REPLAY;
             } else {
                 r3 = __shfl_sync(PDG_FULL, rb3, sl);
                 const int pick = nm > 1 ? (int)__umulhi(r3, (u32)nm) : 0;
@@ -431,8 +533,10 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
             logq = log_q2 - log_q1;
         }
         PT(2)
+        // warp 1 keeps the decisions of ONE pass pending; an iteration with more than eight proposals is
+        // left to warp 0
+        if (SPEC && role == 1 && nm > 8) { spec_ok = false; nm = 0; }
         // ---- score + accept + apply, eight proposals per pass -----------------------------------
-        double log_p = 0.0;
         for (int g0 = 0; g0 < nm; g0 += 8) {
             const int mi = lane >> 2, q = lane & 3, j = g0 + mi;
             const bool valid = j < nm;
@@ -454,7 +558,7 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
             double sc = 0.0;
             if (MODEL != PDG_MODEL_UNIFORM) {
                 const int kq = (q == 0) ? kb : (q == 1) ? ks : (q == 2) ? kb + 1 : ks + 1;
-                errflag |= warp_scores<MODEL, WMAX, LIGHT ? 1 : 4>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, req_sets, req_k);
+                it_err |= warp_scores<MODEL, WMAX, LIGHT ? 1 : (SPEC ? 2 : PDG_NB)>(P, ws, ls, slot, lane, X, valid && kq > 0, sc, it_req_sets, it_req_k);
             }
             PT(4)
             const double sc1 = __shfl_down_sync(PDG_FULL, sc, 1), sc2 = __shfl_down_sync(PDG_FULL, sc, 2),
@@ -481,8 +585,8 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
                 const double dl = log_p2 - log_p1, dp = log_g2 - log_g1;
                 const double tot = (dl + dp) + logq;
                 double u;
-                if (replay_on) u = R.mv_u[R.it_off[(size_t)chain * (R.n_samples + 1) + it] + j];
-                else u = draw_unif_unrolled(P.seed_lo, P.seed_hi, gchain, (u32)it, TAG_MOVE, (u32)U);
+                if (replay_on) u = R.mv_u[R.it_off[(size_t)chain * (R.n_samples + 1) + my] + j];
+                else u = draw_unif_unrolled(P.seed_lo, P.seed_hi, gchain, (u32)my, TAG_MOVE, (u32)U);
                 // accept iff u <= min(1, exp(tot))  (:268,:300).  A single-precision exp brackets the
                 // threshold to 1e-4 relative (its error stays below 2e-5 wherever it does not underflow,
                 // and where it underflows exp(tot) < 2^-53 <= every non-zero u); only a draw inside the
@@ -504,54 +608,76 @@ __global__ void __launch_bounds__(256, LIGHT ? 2 : 1) k_mh_run(const __grid_cons
                 }
             }
             PT(5)
-            // accepted proposals in order: record append, running log-probability, bit flips
             const u32 am = __ballot_sync(PDG_FULL, acc);
             if (am) {
-                if (acc) {
-                    const long long slot_r = nrec + __popc(am & lt);
-                    if (slot_r < P.rec_cap) {
-                        const size_t ro = (size_t)chain * P.rec_cap + slot_r;
-                        pdg_update h;
-                        h.i = (int)it; h.k = (int)(k + j + 1); h.node = (unsigned short)node; h.U = (unsigned short)U;
-                        h.Uadj = (short)Ua; h.type = (unsigned char)mtype; h.pad = 0;
-                        P.rec[ro] = h;
-#pragma unroll
-                        for (int w = 0; w < WMAX; ++w) if (w < W) { P.rec_bits[ro * 2 * W + w] = Cw[w]; P.rec_bits[ro * 2 * W + W + w] = Aw[w]; }
-                    } else if (P.rec_cap > 0) errflag |= ERR_OVERFLOW;      // rec_cap == 0: recording is off
-                    if (k + j + 1 > 2147483647LL) errflag |= ERR_OVERFLOW;     // pdg_update.k is 32 bits wide
-                }
                 u32 rem = am;
                 while (rem) {                                   // :269,:301 log_p += ... in proposal order
                     const int src = __ffs((int)rem) - 1;
                     rem &= rem - 1;
                     log_p += __shfl_sync(PDG_FULL, delta, src);
                 }
-                nrec += __popc(am);
-                __syncwarp();
-                if (acc) {                                      // junction_tree.py:78-100 connect / disconnect
-                    atomicXor(&Mc[(size_t)U * W + (node >> 6)], 1ull << (node & 63));
-                    atomicXor(&Nc[(size_t)node * W + (U >> 6)], 1ull << (U & 63));
+                if (SPEC && role == 1) {
+                    pend_am = am; pend_acc = acc; pend_U = U; pend_Ua = Ua; pend_j = j;
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w) { pend_C[w] = Cw[w]; pend_A[w] = Aw[w]; }
+                } else {
+                    apply_accepts(am, acc, my, k, j, node, mtype, U, Ua, Cw, Aw);
                 }
-                if (!SMEM_STATE) __threadfence();           // the bit flips are performed before any lane reads the rows again
-                __syncwarp();
             }
         }
         PT(6)
-        k += nm;
-        logl_prev = logl_prev + log_p;                      // :304 running sum
-        if (lane == sl) lbuf = logl_prev;
-        if (sl == 31 || it + 1 == it1) {
-            if (lane <= sl) P.logl[(size_t)chain * P.n_samples + (it - sl) + lane] = lbuf;
+        }   // active
+        if (SPEC) {
+            // ---- the pair exchanges what its two iterations did (mailbox double-buffered by round)
+            volatile PairBox *bx = box + (round & 1);
+            const int my_nacc = role == 0 ? (int)(nrec - nrec_round) : __popc(pend_am);
             if (lane == 0) {
-                atomicAdd(&P.work[chain * 16 + 4], (unsigned long long)req_sets);
-                atomicAdd(&P.work[chain * 16 + 5], (unsigned long long)req_k);
+                if (role == 0) { bx->a_nm = nm; bx->a_nacc = my_nacc; bx->a_logp = log_p; }
+                else {
+                    bx->b_nm = nm; bx->b_nacc = my_nacc; bx->b_logp = log_p; bx->b_ok = (active && spec_ok) ? 1 : 0;
+                }
             }
-            req_sets = 0u; req_k = 0u;
+            pair_bar(bar_id);
+            const int a_nm = bx->a_nm, a_nacc = bx->a_nacc, b_nm = bx->b_nm, b_nacc = bx->b_nacc;
+            const double a_logp = bx->a_logp, b_logp = bx->b_logp;
+            const bool commit = bx->b_ok != 0 && a_nacc == 0;
+            // iteration `it` (warp 0 has applied it already)
+            k += a_nm;
+            logl_prev = logl_prev + a_logp;                     // :304 running sum
+            emit_logl(it, logl_prev);
+            if (role == 0) { errflag |= it_err; req_sets += it_req_sets; req_k += it_req_k; }
+            else nrec += a_nacc;
+            if (commit) {
+                // iteration `it + 1`: warp 1 computed it on the very state a sequential run would have seen
+                if (role == 1) {
+                    if (pend_am) apply_accepts(pend_am, pend_acc, my, k, pend_j, node, mtype, pend_U, pend_Ua, pend_C, pend_A);
+                    errflag |= it_err; req_sets += it_req_sets; req_k += it_req_k;
+                } else nrec += b_nacc;
+                k += b_nm;
+                logl_prev = logl_prev + b_logp;
+                emit_logl(it + 1, logl_prev);
+                if (b_nacc) pair_bar(bar_id);                   // the flips are in place before anyone reads the state again
+                it += 2;
+            } else ++it;
+        }
+        if (!SPEC) {
+            k += nm;
+            logl_prev = logl_prev + log_p;                      // :304 running sum
+            emit_logl(it, logl_prev);
+            errflag |= it_err;
+            req_sets += it_req_sets; req_k += it_req_k;
+            ++it;
         }
     }
     __syncwarp();
     PT_FLUSH
-    if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
-    if (lane == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
+    if (role == 0) {
+        if (SMEM_STATE) for (int i = lane; i < p * W; i += 32) { Mg[i] = Mc[i]; Ng[i] = Nc[i]; }
+        if (lane == 0) { P.kcount[chain] = k; P.nrec[chain] = nrec; }
+    }
+    if (lane == 0 && (req_sets | req_k)) {
+        atomicAdd(&P.work[chain * 16 + 4], (unsigned long long)req_sets);
+        atomicAdd(&P.work[chain * 16 + 5], (unsigned long long)req_k);
+    }
     if (errflag) atomicOr(&P.err[chain], errflag);
 }

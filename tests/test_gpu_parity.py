@@ -186,10 +186,13 @@ def test_loglin_scorer_matches_reference():
 
 
 @pytest.mark.parametrize("env", [{"PDG_LIGHT": "0"}, {"PDG_LIGHT": "1"}, {"PDG_FUSED": "1"}, {"PDG_FUSED": "0", "PDG_LOCKSTEP": "0"},
-                                 {"PDG_LL_CAP": "1024", "PDG_LIGHT": "0"}, {"PDG_WPC": "3"}])
+                                 {"PDG_LL_CAP": "1024", "PDG_LIGHT": "0"}, {"PDG_WPC": "3"}, {"PDG_SPEC": "0"},
+                                 {"PDG_SPEC": "1", "PDG_LIGHT": "0"}, {"PDG_SPEC": "1", "PDG_WPC": "2", "PDG_FUSED": "0"},
+                                 {"PDG_RSYNC": "1", "PDG_SPEC": "0", "PDG_LOCKSTEP": "8"}, {"PDG_RSYNC": "0", "PDG_SPEC": "1", "PDG_LOCKSTEP": "4"}])
 def test_kernel_variants_give_identical_chains(monkeypatch, env):
     """The light / regular log-linear kernels, fused / per-launch randomisation, the re-alignment barrier,
-    the shared count-table size and the CTA width are performance knobs: same chains, bit for bit."""
+    the shared count-table size, the CTA width and the two-warps-per-chain speculation are performance knobs:
+    same chains, bit for bit."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     test_production_mode_matches_oracle("cfg3_p15_parallel_s0", 0, 11, 600, 100)
