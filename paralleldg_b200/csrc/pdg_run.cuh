@@ -15,6 +15,10 @@
 #include "pdg_loglin.cuh"
 #include "pdg_randomize.cuh"
 
+#ifndef PDG_KT_RUN
+#define PDG_KT_RUN 8   // sets up to this size are factorised lane-privately (<= PDG_KT), larger ones by the whole warp (p = 50: 12 -> 526, 8 -> 559, 5 -> 558 M proposals/s)
+#endif
+
 // developer-only latency attribution: nvcc -DPDG_PHASE_TIMERS accumulates clock64() deltas of the
 // phases of an iteration into work[6] (phase id in the high bits is not needed: one run per phase
 // selection, chosen with the PDG_PHASE environment variable through P.mvlog_cap's sign bit... no:
@@ -72,7 +76,7 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
     u32 miss = __ballot_sync(PDG_FULL, need && !hit);
     if (miss == 0u) return 0;
     if (MODEL == PDG_MODEL_GGM) {
-        const bool smiss = need && !hit && kq <= PDG_KT;
+        const bool smiss = need && !hit && kq <= PDG_KT_RUN;
         if (__any_sync(PDG_FULL, smiss)) {
             double s_new = 0.0;
             err |= ggm_lane_scores_rolled<WMAX>(P, ws.tri32, ls.idx, lane, X, smiss ? kq : 0, s_new);
