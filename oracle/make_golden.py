@@ -418,6 +418,53 @@ def generators_fixture(ref):
     save("generators", **out)
 
 
+def greenthomas_fixture(ref):
+    """Traces of the reference's Green-Thomas sampler (mh_greenthomas.py:20-233) for the replay tests of
+    paralleldg_b200/mh_greenthomas.py: czech (log-linear, p = 6), an AR(1-5) Gaussian data set (p = 12)
+    and the uniform model (p = 8)."""
+    import gzip
+    import json
+
+    def plain(o):
+        if isinstance(o, dict):
+            return {str(k): plain(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [plain(v) for v in o]
+        if isinstance(o, (np.integer,)):
+            return int(o)
+        if isinstance(o, (np.floating,)):
+            return float(o)
+        return o
+
+    def dump(name, log, **extra):
+        out = dict(plain(log))
+        out.pop("graphs")
+        out["final_graph"] = plain(log["graphs"][-1])
+        out["n_graph_changes"] = int(sum(1 for a, b in zip(log["graphs"][:-1], log["graphs"][1:]) if a != b))
+        out.update(plain(extra))
+        path = os.path.join(GOLD, name + ".json.gz")
+        with gzip.open(path, "wt") as f:
+            json.dump(out, f, separators=(",", ":"))
+        print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024.0))
+
+    df = pd.read_csv(os.path.join(REFDATA, "czech_autoworkers.csv"), sep=",", header=[0, 1])
+    nl = np.array(df.columns.get_level_values(1), dtype=int)
+    levels = np.array([list(range(l)) for l in nl], dtype=object)
+    sd = ref.seqdist.LogLinearJTPosterior()
+    sd.init_model(df.to_numpy(), 1.0, levels, {})
+    log, _ = rs.trace_greenthomas(1500, 100, sd, 3)
+    dump("greenthomas_czech_s3", log, model="loglin", data=df.to_numpy().astype(int).tolist(), levels=nl.tolist(),
+         pseudo_obs=1.0, n_samples=1500, randomize=100)
+    X, adj, cov = ar_data(ref, 12, 60, seed=12)
+    sd = ref.seqdist.GGMJTPosterior()
+    sd.init_model(np.asmatrix(X), np.identity(12), 1.0, {})
+    log, _ = rs.trace_greenthomas(1500, 50, sd, 5)
+    dump("greenthomas_ggm12_s5", log, model="ggm", data=X.tolist(), delta=1.0, n_samples=1500, randomize=50)
+    sd = ref.seqdist.UniformJTDistribution(8)
+    log, _ = rs.trace_greenthomas(1200, 40, sd, 7)
+    dump("greenthomas_uniform8_s7", log, model="uniform", p=8, n_samples=1200, randomize=40)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = rs.load_reference()
@@ -466,6 +513,8 @@ def main():
         from paralleldg_b200 import datagen
         data, lv, adj = datagen.loglin_ar_data(62, 6000, seed=62)
         loglin_case(ref, "loglin62_parallel_s1", data, lv, "parallel", 1500, 100, 1)
+    if want("greenthomas"):
+        greenthomas_fixture(ref)
     if want("generators"):
         generators_fixture(ref)
     if want("czech_posterior"):

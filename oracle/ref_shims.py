@@ -444,3 +444,154 @@ def run_chain(kind, n_samples, randomize, sd, sd_graph, seed, init_graph=None):
             return fn(n_samples, randomize, sd, sd_graph, init_graph=init_graph, seed=seed)
     finally:
         ref.mh.tqdm = saved
+
+
+def trace_greenthomas(n_samples, randomize, sd, seed):
+    """One chain of the reference's Green-Thomas sampler (mh_greenthomas.py:20-233) with every proposal
+    logged: the junction tree before the move (cliques, edges), the move's own choices (clique / edge,
+    X, Y, the coin flips of disconnect case a), the case letter, both proposal log-probabilities, the
+    log targets and the accept draw; the tree after every randomisation.  Logging wraps
+    aglib.connect_move / disconnect_move / connect_logprob / disconnect_logprob_* and
+    np.random.choice; it draws nothing itself, so the chain is the untraced one."""
+    import contextlib
+    import io
+    ref = load_reference()
+    postprocess_shims()
+    import parallelDG.mh_greenthomas as gt
+    import parallelDG.graph.greenthomas as aglib
+    import parallelDG.graph.junction_tree as jtlib
+    log = {"moves": {}, "randomized": {}}
+    cur = {}
+
+    def snap(tree):
+        return [sorted(c) for c in tree.nodes()], [(sorted(a), sorted(b)) for a, b in tree.edges()]
+
+    orig = dict(conn=aglib.connect_move, disc=aglib.disconnect_move, sel_c=aglib.connect_select_subsets,
+                sel_d=aglib.disconnect_select_subsets, rs=aglib.aux.random_subset, clp=aglib.connect_logprob,
+                dla=aglib.disconnect_logprob_a, dlb=aglib.disconnect_logprob_bcd, rand=jtlib.randomize,
+                choice=np.random.choice, tqdm=gt.tqdm)
+    state = {"i": 0, "in_move": False}
+
+    def begin(kind, tree):
+        nodes, edges = snap(tree)
+        cur.clear()
+        cur.update(kind=kind, nodes=nodes, edges=edges, case=None, X=[], Y=[], with_x=[], log_q12=None, log_q21=None)
+
+    def connect_move(tree):
+        begin("connect", tree)
+        r = orig["conn"](tree)
+        if r:
+            cur["case"], cur["log_q12"] = r[0], float(r[1])
+        return r
+
+    def disconnect_move(tree):
+        begin("disconnect", tree)
+        r = orig["disc"](tree)
+        if r is not False:
+            cur["case"], cur["log_q12"] = r[0], float(r[1])
+        return r
+
+    def sel_c(tree):
+        X, Y, CX, CY = orig["sel_c"](tree)
+        cur.update(X=sorted(X), Y=sorted(Y), CX=sorted(CX), CY=sorted(CY))
+        return X, Y, CX, CY
+
+    def sel_d(tree, c):
+        X, Y = orig["sel_d"](tree, c)
+        cur.update(X=sorted(X), Y=sorted(Y), C=sorted(c))
+        return X, Y
+
+    def random_subset(A):
+        r = orig["rs"](A)
+        cur["with_x"] = [sorted(n) for n in r]
+        return r
+
+    # the reverse-move probability is whichever of these is called from sample_trajectory after the move
+    def wrap_rev(f):
+        def g(*a, **k):
+            v = f(*a, **k)
+            if state["in_move"] is False:
+                cur["log_q21"] = float(v)
+            return v
+        return g
+
+    def conn_guard(f):
+        def g(tree):
+            state["in_move"] = True
+            try:
+                return f(tree)
+            finally:
+                state["in_move"] = False
+        return g
+
+    def randomize_tree(tree):
+        orig["rand"](tree)
+        log["randomized"][state["i"]] = snap(tree)
+
+    def choice(a, size=None, replace=True, p=None):
+        r = orig["choice"](a, size=size, replace=replace, p=p)
+        if p is not None and isinstance(a, (int, np.integer)) and a == 2 and len(p) == 2:
+            cur["accepted"] = int(np.asarray(r).ravel()[0])
+            cur["alpha"] = float(p[1])
+        return r
+
+    class Seq(object):
+        """the iteration range: tells the tracer the MCMC index and files the finished proposal"""
+        def __init__(self, rng):
+            self.rng = rng
+
+        def __iter__(self):
+            for i in self.rng:
+                state["i"] = i
+                cur.clear()
+                cur.update(kind=None, case=None)
+                yield i
+                log["moves"][i] = dict(cur)
+
+    aglib.connect_move = conn_guard(connect_move)
+    aglib.disconnect_move = conn_guard(disconnect_move)
+    aglib.connect_select_subsets = sel_c
+    aglib.disconnect_select_subsets = sel_d
+    aglib.aux.random_subset = random_subset
+    aglib.connect_logprob = wrap_rev(orig["clp"])
+    aglib.disconnect_logprob_a = wrap_rev(orig["dla"])
+    aglib.disconnect_logprob_bcd = wrap_rev(orig["dlb"])
+    jtlib.randomize = randomize_tree
+    np.random.choice = choice
+    gt.tqdm = lambda rng, **k: Seq(rng)
+    # log target after the move = sd.log_likelihood(jt) - log_n_junction_trees(jt, seps)  (:67, :73, :146)
+    orig_ll, orig_mu = sd.log_likelihood, jtlib.log_n_junction_trees
+
+    def log_likelihood(jt):
+        v = orig_ll(jt)
+        cur["ll_after"] = float(v)
+        return v
+
+    def log_mu(tree, S):
+        v = orig_mu(tree, S)
+        cur["mu_after"] = float(v)
+        return v
+    sd.log_likelihood = log_likelihood
+    jtlib.log_n_junction_trees = log_mu
+    try:
+        np.random.seed(seed)
+        random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            traj = gt.sample_trajectory(n_samples, randomize, sd, seed=seed)
+    finally:
+        aglib.connect_move, aglib.disconnect_move = orig["conn"], orig["disc"]
+        aglib.connect_select_subsets, aglib.disconnect_select_subsets = orig["sel_c"], orig["sel_d"]
+        aglib.aux.random_subset = orig["rs"]
+        aglib.connect_logprob, aglib.disconnect_logprob_a, aglib.disconnect_logprob_bcd = orig["clp"], orig["dla"], orig["dlb"]
+        jtlib.randomize = orig["rand"]
+        np.random.choice = orig["choice"]
+        gt.tqdm = orig["tqdm"]
+        del sd.log_likelihood
+        jtlib.log_n_junction_trees = orig_mu
+    log["logl"] = [float(x) for x in traj.logl]
+    log["graphs"] = [sorted(tuple(sorted((int(a), int(b)))) for a, b in g.edges()) for g in traj.trajectory]
+    for i, mv in log["moves"].items():
+        mv["log_p1"] = log["logl"][i - 1]
+        if "ll_after" in mv:
+            mv["log_p2"] = mv["ll_after"] - mv["mu_after"]
+    return log, traj
