@@ -366,7 +366,7 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
             return e;
         };
         void *d_data = nullptr, *d_lv = nullptr, *d_k = nullptr, *d_a = nullptr, *d_lg = nullptr;
-        void *d_hist = nullptr, *d_lock = nullptr, *d_hk = nullptr, *d_hc = nullptr, *d_cc = nullptr;
+        void *d_hist = nullptr, *d_lock = nullptr, *d_hk = nullptr, *d_hc = nullptr, *d_cc = nullptr, *d_list = nullptr;
         CK(own(data_bytes, &d_data));
         CK(own((size_t)P.p * sizeof(int), &d_lv));
         CK(own((size_t)(n_ktab > 0 ? n_ktab : 1) * 8, &d_k));
@@ -377,16 +377,18 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
         CK(own((size_t)sp.nsp * hs * 8, &d_hk));
         CK(own((size_t)sp.nsp * hs * 4, &d_hc));
         CK(own((size_t)sp.nsp * (size_t)(nrows + 2) * 4, &d_cc));
+        CK(own((size_t)sp.nsp * (size_t)(nrows + 1) * 4, &d_list));
         CK(cudaMemsetAsync(d_data, 0, data_bytes, ctx->stream));
         CK(cudaMemsetAsync(d_hist, 0, (size_t)2 * P.n_chains * hist_cells * 4, ctx->stream));
         CK(cudaMemsetAsync(d_lock, 0, (size_t)sp.nsp * 4, ctx->stream));
         CK(cudaMemsetAsync(d_hk, 0, (size_t)sp.nsp * hs * 8, ctx->stream));
         CK(cudaMemsetAsync(d_hc, 0, (size_t)sp.nsp * hs * 4, ctx->stream));
         CK(cudaMemsetAsync(d_cc, 0, (size_t)sp.nsp * (size_t)(nrows + 2) * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_list, 0, (size_t)sp.nsp * (size_t)(nrows + 1) * 4, ctx->stream));
         P.data = (const unsigned char *)d_data; P.levels = (const int *)d_lv;
         P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
         P.hist = (unsigned int *)d_hist;
-        sp.lock = (int *)d_lock; sp.hkeys = (u64 *)d_hk; sp.hcnt = (unsigned int *)d_hc; sp.cc = (unsigned int *)d_cc;
+        sp.lock = (int *)d_lock; sp.hkeys = (u64 *)d_hk; sp.hcnt = (unsigned int *)d_hc; sp.cc = (unsigned int *)d_cc; sp.list = (int *)d_list;
         P.sp = sp;
         for (int q = 0; q < 4; ++q) ctx->ll_shape[q] = shape[q];
     }

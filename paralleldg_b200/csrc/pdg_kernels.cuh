@@ -33,6 +33,7 @@ struct LoglinSparse {
     u64 *hkeys;             // [nsp][hslots]
     unsigned int *hcnt;     // [nsp][hslots]
     unsigned int *cc;       // [nsp][nrows + 2] count-of-counts
+    int *list;              // [nsp][nrows + 1] slots taken by the scan in progress; entry 0 = how many
     int nsp, hslots;
 };
 
@@ -237,7 +238,9 @@ __device__ __forceinline__ double ggm_score_from(const PdgParams &P, int k, doub
 __host__ __device__ inline int tri_bytes_for(int ll_cap) { return ll_cap > 0 ? (ll_cap + 48) * 4 : 528 * 8; }
 
 // per-warp scratch: packed 32x32 triangle + index list
+struct HelpBox;
 struct WarpScratch {
+    HelpBox *help;            // log-linear MH kernel: the CTA's scan-sharing mailbox (pdg_loglin.cuh), else null
     double *tri32;            // 528 doubles, or the log-linear count table (shared)
     short *idx;               // p + 1 entries (shared)
     double *big;              // global scratch for k > 32 (may be null)

@@ -40,6 +40,24 @@ struct ScoreRes { double score; int err; };
 // Counting: shared-memory reductions into R interleaved replicas of the table (R * K <= cap; lanes
 // l and l + R share one, so same-cell collisions inside a warp mostly disappear), or this warp's
 // table in global memory above `cap` cells.
+// A scan offered to the idle warps of the CTA (warps whose chain has ended): the rows are dealt out in
+// chunks through a ticket that carries the request number, every participant counts into its own
+// table (same layout) and adds it to the requester's, and the requester waits until all chunks are
+// accounted for.  Counts are integers, so the table -- and the score -- do not depend on who counted what.
+#define PDG_HELP_ROWS 4096          // rows per chunk (a multiple of 512 * NB)
+struct HelpBox {
+    int lock;                       // 1 while a request is open
+    int ticket;                     // (request number << 16) | next chunk
+    int n_chunks, done;             // chunks of the open request / chunks counted AND merged
+    int finished;                   // chains of the CTA that have ended
+    int mode, glb, nslots, slotsA, rshift;
+    unsigned int mulA, mulB, cells; // cells: counters of the (replicated) shared table
+    unsigned int *req_table;        // the requester's shared table
+    unsigned int *hist;             // the requester's table in global memory (glb)
+    long long n, ld;
+    unsigned int colinfo[32];       // multipliers and column ids by slot
+};
+
 struct LlCount {
     int nslots, slotsA;         // column slots in use (multiple of 4), slots of the first group
     unsigned int mulA, mulB;    // shared: byte strides of codeA / codeB; global: KB, 1
@@ -54,9 +72,10 @@ __device__ __forceinline__ void ll_red_shared(unsigned int addr)
 
 // NB = 512-row blocks per warp pass (4: 16 loads in flight per lane; 1 for the light MH kernel)
 template <int MODE, bool GLB, int NB>
-__device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long long ld, long long n, LlCount q,
+__device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long long ld, long long b0, long long n, LlCount q,
                                                    const unsigned int *colinfo, int lane)
 {
+    // rows [b0, n); b0 is a multiple of 512 * NB
     constexpr int NC = MODE == 0 ? 1 : 2;
     uint4 x[4][NB];
     auto issue = [&](long long base, int j0) {
@@ -75,8 +94,8 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
             if (MODE == 1) ll_red_shared(a * q.mulA + (b * q.mulB + q.sbase)); else ll_red_shared(a * q.mulA + q.sbase);
         }
     };
-    issue(0, 0);
-    for (long long base = 0; base < n; base += 512 * NB) {
+    issue(b0, 0);
+    for (long long base = b0; base < n; base += 512 * NB) {
         unsigned int c[NB][4][NC];
 #pragma unroll
         for (int u = 0; u < NB; ++u)
@@ -214,6 +233,73 @@ __device__ __forceinline__ double loglin_derive(const LoglinArgs &P, const WarpS
     return sc;
 }
 
+// counts the chunks of request `seq` this warp manages to take, into the table `q` describes; returns how many
+template <int NB>
+static __device__ __noinline__ int help_chunks(HelpBox *hb, int seq, const unsigned char *D, LlCount q,
+                                               const unsigned int *colinfo, int lane)
+{
+    const int mode = hb->mode, glb = hb->glb, n_chunks = hb->n_chunks;
+    const long long n = hb->n, ld = hb->ld;
+    int mine = 0;
+    for (;;) {
+        int c = -1;
+        if (lane == 0) {
+            for (;;) {
+                const int old = *(volatile int *)&hb->ticket;
+                if ((old >> 16) != seq || (old & 0xffff) >= n_chunks) break;
+                if (atomicCAS(&hb->ticket, old, old + 1) == old) { c = old & 0xffff; break; }
+            }
+        }
+        c = __shfl_sync(PDG_FULL, c, 0);
+        if (c < 0) break;
+        const long long b0 = (long long)c * PDG_HELP_ROWS;
+        const long long b1 = (b0 + PDG_HELP_ROWS < n) ? b0 + PDG_HELP_ROWS : n;
+        if (mode == 0) loglin_count_dense<0, false, NB>(D, ld, b0, b1, q, colinfo, lane);
+        else if (!glb) loglin_count_dense<1, false, NB>(D, ld, b0, b1, q, colinfo, lane);
+        else loglin_count_dense<1, true, NB>(D, ld, b0, b1, q, colinfo, lane);
+        ++mine;
+    }
+    return mine;
+}
+
+// what a warp does once its own chain has ended: serve the scans of the CTA's other chains until all
+// of them have ended (`live_warps` chains in this CTA)
+template <int NB>
+__device__ __forceinline__ void help_until_done(HelpBox *hb, const unsigned char *D, unsigned int *sh, int cap, int live_warps, int lane)
+{
+    if (lane == 0) atomicAdd(&hb->finished, 1);
+    for (;;) {
+        int fin = 0, t = 0, open = 0;
+        if (lane == 0) { fin = *(volatile int *)&hb->finished; t = *(volatile int *)&hb->ticket; open = *(volatile int *)&hb->lock; }
+        fin = __shfl_sync(PDG_FULL, fin, 0); t = __shfl_sync(PDG_FULL, t, 0); open = __shfl_sync(PDG_FULL, open, 0);
+        if (fin >= live_warps) break;
+        const int seq = t >> 16;
+        if (!open || seq == 0 || (t & 0xffff) >= *(volatile int *)&hb->n_chunks) { __nanosleep(1000); continue; }
+        // (the request's fields were written before its ticket; a stale read fails the ticket's compare-and-swap)
+        const int glb = *(volatile int *)&hb->glb, rshift = *(volatile int *)&hb->rshift;
+        const unsigned int cells = *(volatile unsigned int *)&hb->cells;
+        if (!glb && (cells == 0u || cells > (unsigned int)cap)) { __nanosleep(1000); continue; }
+        LlCount q;
+        q.nslots = *(volatile int *)&hb->nslots; q.slotsA = *(volatile int *)&hb->slotsA;
+        q.mulA = *(volatile unsigned int *)&hb->mulA; q.mulB = *(volatile unsigned int *)&hb->mulB;
+        q.hist = *(unsigned int * volatile *)&hb->hist;
+        q.sbase = (unsigned int)__cvta_generic_to_shared(sh) + 4u * (unsigned int)(lane & ((1 << rshift) - 1));
+        if (!glb) for (unsigned int c = lane; c < cells; c += 32) sh[c] = 0u;
+        __syncwarp();
+        const int mine = help_chunks<NB>(hb, seq, D, q, hb->colinfo, lane);
+        __syncwarp();
+        if (mine) {
+            if (!glb) {
+                unsigned int *dst = *(unsigned int * volatile *)&hb->req_table;
+                for (unsigned int c = lane; c < cells; c += 32) { const unsigned int v = sh[c]; if (v) atomicAdd(&dst[c], v); }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&hb->done, mine);
+        }
+    }
+}
+
 template <int WMAX, int NB>
 __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, int slot, KeyW<WMAX> XK, int lane, LlTable &tout)
 {
@@ -274,11 +360,44 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
         q.sbase = (unsigned int)__cvta_generic_to_shared(sh) + 4u * (unsigned int)(lane & (R - 1));
         if (glb) { q.mulA = mode == 1 ? prodB : 1u; q.mulB = 1u; }
         else { q.mulB = 4u << rshift; q.mulA = mode == 1 ? prodB * q.mulB : q.mulB; }
-        if (mode == 0) loglin_count_dense<0, false, NB>(D, P.ld, n, q, colinfo, lane);
-        else if (mode == 1 && !glb) loglin_count_dense<1, false, NB>(D, P.ld, n, q, colinfo, lane);
-        else if (mode == 1) loglin_count_dense<1, true, NB>(D, P.ld, n, q, colinfo, lane);
-        else if (!glb) loglin_count_dense<2, false, NB>(D, P.ld, n, q, colinfo, lane);
-        else loglin_count_dense<2, true, NB>(D, P.ld, n, q, colinfo, lane);
+        // large scans are offered to the warps of the CTA whose chains have ended (MH kernel only)
+        HelpBox *hb = ws.help;
+        bool coop = false;
+        if (hb && mode != 2 && n >= 4 * PDG_HELP_ROWS) {
+            int got = 0;
+            // (only once some chain of the CTA has ended: the chunked pass gives up the prefetch across chunk ends)
+            if (lane == 0 && *(volatile int *)&hb->finished > 0) got = atomicCAS(&hb->lock, 0, 1) == 0 ? 1 : 0;
+            coop = __shfl_sync(PDG_FULL, got, 0) != 0;
+        }
+        if (coop) {
+            hb->colinfo[lane] = colinfo[lane];
+            __syncwarp();
+            int seq = 0;
+            if (lane == 0) {
+                hb->mode = mode; hb->glb = glb ? 1 : 0; hb->nslots = q.nslots; hb->slotsA = q.slotsA; hb->rshift = rshift;
+                hb->mulA = q.mulA; hb->mulB = q.mulB; hb->cells = glb ? 0u : ((unsigned int)Ki << rshift);
+                hb->req_table = sh; hb->hist = hist; hb->n = n; hb->ld = P.ld;
+                hb->n_chunks = (int)((n + PDG_HELP_ROWS - 1) / PDG_HELP_ROWS); hb->done = 0;
+                seq = ((*(volatile int *)&hb->ticket >> 16) + 1) & 0x7fff;
+                if (seq == 0) seq = 1;
+                __threadfence_block();
+                *(volatile int *)&hb->ticket = seq << 16;            // published last
+            }
+            seq = __shfl_sync(PDG_FULL, seq, 0);
+            __syncwarp();
+            const int mine = help_chunks<NB>(hb, seq, D, q, colinfo, lane);
+            if (lane == 0) {
+                atomicAdd(&hb->done, mine);
+                while (*(volatile int *)&hb->done < hb->n_chunks) __nanosleep(200);
+                __threadfence_block();
+                *(volatile int *)&hb->lock = 0;
+            }
+            __syncwarp();
+        } else if (mode == 0) loglin_count_dense<0, false, NB>(D, P.ld, 0, n, q, colinfo, lane);
+        else if (mode == 1 && !glb) loglin_count_dense<1, false, NB>(D, P.ld, 0, n, q, colinfo, lane);
+        else if (mode == 1) loglin_count_dense<1, true, NB>(D, P.ld, 0, n, q, colinfo, lane);
+        else if (!glb) loglin_count_dense<2, false, NB>(D, P.ld, 0, n, q, colinfo, lane);
+        else loglin_count_dense<2, true, NB>(D, P.ld, 0, n, q, colinfo, lane);
         __syncwarp();
         if (!glb) {
             // fold the replicas into a compact table sh[0 .. Ki) (32 cells at a time: all reads of a
@@ -329,37 +448,111 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     s = __shfl_sync(PDG_FULL, s, 0);
     u64 *hk = S.hkeys + (size_t)s * S.hslots;
     unsigned int *hc = S.hcnt + (size_t)s * S.hslots, *cc = S.cc + (size_t)s * (size_t)(n + 2);
+    int *list = S.list + (size_t)s * (size_t)(n + 1);          // list[0] = 0 on entry
     const u32 hmask = (u32)S.hslots - 1u;
-    for (long long r = lane; r < n; r += 32) {
-        u64 c = 0ull;
-        for (int j = 0; j < k; ++j) { const int g = ws.idx[j]; c = c * (u64)P.levels[g] + D[(size_t)g * (size_t)P.ld + r]; }
-        const u64 key = c + 1ull;
-        u32 h = (u32)mix64(key) & hmask;
-        for (;;) {
-            const u64 old = atomicCAS(&hk[h], 0ull, key);
-            if (old == 0ull || old == key) { atomicAdd(&hc[h], 1u); break; }
-            h = (h + 1) & hmask;
+    // Keys: every lane builds the mixed-radix codes of 16 consecutive rows from one 16-byte load per column
+    // (a warp pass covers 512 rows), four columns' loads in flight; missing columns of the last group read
+    // the zero column with multiplier 1, as in the dense pass.  (One row per lane and one byte per load, with
+    // the multiply-add chain waiting for every load in turn, took 14 ms per 17-column scan.)
+    // Insertion: cells of a clique's table are concentrated, so lanes holding the same key are merged first
+    // (match.any: one leader adds the group's count), and a slot that already holds the key is found by a
+    // plain L2 read -- eight in flight -- with the count added fire-and-forget; only a key's first insertion
+    // waits for a compare-and-swap and records its slot in the list.
+    for (long long base = 0; base < n; base += 512) {
+        const long long r0 = base + lane * 16;
+        u64 keys[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) keys[i] = 0ull;
+        uint4 x[4], xn[4];
+        u64 Lc[4], Ln[4];
+        auto load_group = [&](int j0, uint4 (&xx)[4], u64 (&LL)[4]) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = j0 + jj;
+                const int g = j < k ? (int)ws.idx[j] : P.zero_col;
+                LL[jj] = j < k ? (u64)__ldg(&P.levels[g]) : 1ull;
+                xx[jj] = __ldg((const uint4 *)(D + (size_t)g * (size_t)P.ld + r0));
+            }
+        };
+        load_group(0, x, Lc);
+        for (int j0 = 0; j0 < k; j0 += 4) {
+            if (j0 + 4 < k) load_group(j0 + 4, xn, Ln);          // the next group's loads fly while this one is folded in
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const unsigned int w4[4] = {x[jj].x, x[jj].y, x[jj].z, x[jj].w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) keys[i] = keys[i] * Lc[jj] + (u64)((w4[i >> 2] >> (8 * (i & 3))) & 0xffu);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) { x[jj] = xn[jj]; Lc[jj] = Ln[jj]; }
+        }
+#pragma unroll
+        for (int i0 = 0; i0 < 16; i0 += 8) {
+            u64 key[8], cur[8];
+            u32 hh[8], cnt[8];
+            bool lead[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                key[u] = (r0 + i0 + u < n) ? keys[i0 + u] + 1ull : 0ull;      // 0: no row
+                const u32 m = __match_any_sync(PDG_FULL, key[u]);
+                lead[u] = key[u] != 0ull && (int)(__ffs((int)m) - 1) == lane;
+                cnt[u] = (u32)__popc(m);
+                hh[u] = (u32)mix64(key[u]) & hmask;
+                cur[u] = lead[u] ? __ldcg(&hk[hh[u]]) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (!lead[u]) continue;
+                u32 h = hh[u];
+                u64 c = cur[u];
+                for (;;) {
+                    if (c == 0ull) {
+                        c = atomicCAS(&hk[h], 0ull, key[u]);
+                        if (c == 0ull) list[1 + atomicAdd(&list[0], 1)] = (int)h;      // a new cell: remember its slot
+                    }
+                    if (c == 0ull || c == key[u]) { atomicAdd(&hc[h], cnt[u]); break; }
+                    h = (h + 1) & hmask;
+                    c = __ldcg(&hk[h]);
+                }
+            }
         }
     }
     __threadfence();
     __syncwarp();
+    // the occupied slots come off the list (a few thousand cells), not off a pass over the whole table
+    const int ncell = *(volatile int *)&list[0];
     unsigned int maxc = 0;
-    for (int h = lane; h < S.hslots; h += 32) {
-        if (__ldcg(&hk[h]) != 0ull) {
-            const unsigned int c = __ldcg(&hc[h]);
-            atomicAdd(&cc[c], 1u);
-            maxc = c > maxc ? c : maxc;
-            hk[h] = 0ull; hc[h] = 0u;
+    for (int i0 = 0; i0 < ncell; i0 += 128) {
+        int hx[4];
+        unsigned int cx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u + lane; hx[u] = i < ncell ? __ldcg(&list[1 + i]) : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cx[u] = hx[u] >= 0 ? __ldcg(&hc[hx[u]]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (hx[u] < 0) continue;
+            atomicAdd(&cc[cx[u]], 1u);
+            maxc = cx[u] > maxc ? cx[u] : maxc;
+            hk[hx[u]] = 0ull; hc[hx[u]] = 0u;
         }
     }
     maxc = __reduce_max_sync(PDG_FULL, maxc);
     __threadfence();
     __syncwarp();
-    for (unsigned int c = 1 + lane; c <= maxc; c += 32) {
-        const unsigned int m = __ldcg(&cc[c]);
-        if (m) {
-            acc += (double)m * (LG ? LG[c] : (lgamma((double)c + alpha) - lga));
-            cc[c] = 0u;
+    if (lane == 0) list[0] = 0;
+    // count-of-counts in ascending count order (order-free sum), four loads in flight per lane
+    for (unsigned int c0 = 1; c0 <= maxc; c0 += 128) {
+        unsigned int mx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const unsigned int c = c0 + 32 * u + lane; mx[u] = c <= maxc ? __ldcg(&cc[c]) : 0u; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int c = c0 + 32 * u + lane;
+            if (mx[u]) {
+                acc += (double)mx[u] * (LG ? LG[c] : (lgamma((double)c + alpha) - lga));
+                cc[c] = 0u;
+            }
         }
     }
     __threadfence();
@@ -367,6 +560,9 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     if (lane == 0) atomicExch(&S.lock[s], 0);
     score = warp_sum(acc) - constK;
     res.score = score;
+#ifdef PDG_PHASE_TIMERS
+    if (lane == 0) { atomicAdd(&g_kh[0][k < 31 ? k : 31], 1ull); atomicAdd(&g_kh[1][k < 31 ? k : 31], (unsigned long long)(clock64() - kh_t0)); }
+#endif
     return res;
 }
 

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
     unsigned short *s_nu = (unsigned short *)(smem + L.off_nu);
     unsigned char *s_first = smem + L.off_first;
     WarpScratch ws;
+    ws.help = nullptr;
     ws.tri32 = (double *)(smem + L.off_tri);
     ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     extern __shared__ __align__(16) unsigned char smem[];
     const int W = P.W, lane = threadIdx.x;
     WarpScratch ws;
+    ws.help = nullptr;
     LaneScratch ls;
     ws.tri32 = (double *)smem;
     ls.unused = 0;

@@ -198,6 +198,15 @@ k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin, long
          const __grid_constant__ PdgReplayDev R, int lockstep, RandScratch Z, long long randomize, int smem_per_warp)
 {
     extern __shared__ __align__(16) unsigned char smem_all[];
+    // log-linear chains with long tables: warps whose chain has ended serve the scans of the CTA's other
+    // chains (pdg_loglin.cuh HelpBox) -- the run ends with its slowest chain, and that chain's scans are
+    // the one thing the idle warps can take off its critical path
+    constexpr bool HELP = MODEL == PDG_MODEL_LOGLIN && !LIGHT && !SPEC && !DIAG;
+    __shared__ HelpBox s_help;
+    if (HELP) {
+        if (threadIdx.x == 0) { s_help.lock = 0; s_help.ticket = 0; s_help.n_chunks = 0; s_help.done = 0; s_help.finished = 0; }
+        __syncthreads();
+    }
     const int p = P.p, W = P.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int role = SPEC ? (warp & 1) : 0;                 // 1 = the speculating warp of a pair
@@ -226,6 +235,7 @@ k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin, long
     volatile PairBox *box = (volatile PairBox *)(smem_c + L.off_pair);
     const int bar_id = 1 + cw;
     WarpScratch ws;
+    ws.help = HELP ? &s_help : nullptr;
     ws.tri32 = (double *)(smem + L.off_tri);
     ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;
@@ -684,4 +694,8 @@ k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin, long
         atomicAdd(&P.work[chain * 16 + 5], (unsigned long long)req_k);
     }
     if (errflag) atomicOr(&P.err[chain], errflag);
+    if (HELP) {
+        __syncwarp();
+        help_until_done<LIGHT ? 1 : PDG_NB>(&s_help, P.data, (unsigned int *)ws.tri32, P.ll_cap, live_threads >> 5, lane);
+    }
 }
