@@ -391,6 +391,13 @@ extern "C" int pdg_debug_loglin_kh(unsigned long long *out)
 }
 #endif
 
+#if defined(PDG_PHASE_TIMERS) && defined(PDG_TU_IS_GGM)
+extern "C" int pdg_debug_ggm_kg(unsigned long long *out)
+{
+    return cudaMemcpyFromSymbol(out, g_kg, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 #define PDG_CAT2(a, b) a##b
 #define PDG_CAT(a, b) PDG_CAT2(a, b)
 

@@ -15,6 +15,9 @@
 #include "pdg_loglin.cuh"
 #include "pdg_randomize.cuh"
 
+#ifdef PDG_PHASE_TIMERS
+static __device__ unsigned long long g_kg[2][64];     // developer probe: cooperative GGM scores and cycles by set size; [.][0] = lane-private passes
+#endif
 #ifndef PDG_KT_RUN
 #define PDG_KT_RUN 8   // sets up to this size are factorised lane-privately (<= PDG_KT), larger ones by the whole warp (p = 50: 12 -> 526, 8 -> 559, 5 -> 558 M proposals/s)
 #endif
@@ -79,7 +82,14 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
         const bool smiss = need && !hit && kq <= PDG_KT_RUN;
         if (__any_sync(PDG_FULL, smiss)) {
             double s_new = 0.0;
+#ifdef PDG_PHASE_TIMERS
+            const long long lp_t0 = clock64();
+#endif
             err |= ggm_lane_scores_rolled<WMAX>(P, ws.tri32, ls.idx, lane, X, smiss ? kq : 0, s_new);
+#ifdef PDG_PHASE_TIMERS
+            const u32 lp_m = __ballot_sync(PDG_FULL, smiss);
+            if (lane == 0) { atomicAdd(&g_kg[0][0], (unsigned long long)__popc(lp_m)); atomicAdd(&g_kg[1][0], (unsigned long long)(clock64() - lp_t0)); }
+#endif
             if (smiss) {
                 score = s_new; hit = true;
                 memo_insert<WMAX>(P.memo, X, W, s_new);
@@ -103,8 +113,20 @@ __device__ __forceinline__ int warp_scores(const PdgParams &P, const WarpScratch
         double sc = 0.0;
         int e;
         LlTable tab; tab.cells = 0u; tab.k = 0;
+#ifdef PDG_PHASE_TIMERS
+        const long long ggm_t0 = clock64();
+#endif
         if (MODEL == PDG_MODEL_GGM) e = ggm_set_score<WMAX>(P, ws, Y, lane, sc);
         else e = loglin_set_score<WMAX, NB>(P, ws, slot, Y, lane, sc, tab);
+#ifdef PDG_PHASE_TIMERS
+        if (MODEL == PDG_MODEL_GGM && lane == 0) {
+            int kk = 0;
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w) kk += __popcll(Y[w]);
+            kk = kk < 63 ? kk : 63;
+            atomicAdd(&g_kg[0][kk], 1ull); atomicAdd(&g_kg[1][kk], (unsigned long long)(clock64() - ggm_t0));
+        }
+#endif
         err |= e;
         if (lane == 0) {
             if (!e) memo_insert<WMAX>(P.memo, Y, W, sc);
