@@ -162,6 +162,7 @@ int pdg_create(pdg_ctx **out, int device, int p, int64_t n_chains, uint32_t chai
     P.n_chains = n_chains; P.chain0 = chain0; P.seed_lo = (u32)seed; P.seed_hi = (u32)(seed >> 32);
     P.n_samples = n_samples; P.rec_cap = rec_cap;
     P.memo_small = getenv("PDG_NO_MEMO_SMALL") ? 0 : 1;
+    P.tri_extra = 0; P.ktri_run = 32;
     const size_t C = (size_t)n_chains, pw = (size_t)p * P.W;
     cudaError_t e = cudaSuccess;
 #define TRY(x) if (e == cudaSuccess) e = (x)
@@ -287,7 +288,7 @@ int pdg_set_prior(pdg_ctx *ctx, int prior_kind, double a, double b)
 int pdg_set_model_uniform(pdg_ctx *ctx)
 {
     if (!ctx) return PDG_E_ARG;
-    ctx->P.model = PDG_MODEL_UNIFORM; ctx->P.ll_cap = 0;
+    ctx->P.model = PDG_MODEL_UNIFORM; ctx->P.ll_cap = 0; ctx->P.tri_extra = 0; ctx->P.ktri_run = 32;
     ctx->model_set = true;
     return memo_clear(ctx);                 // cached scores belong to the model that produced them
 }
@@ -325,6 +326,20 @@ int pdg_set_model_ggm(pdg_ctx *ctx, const void *A, const void *D, int64_t n, dou
     P.A = ctx->d_A; P.Dm = ctx->d_D; P.logDdiag = ctx->d_logD; P.gconst = ctx->d_gconst;
     P.delta = delta; P.nobs = (double)n;
     P.model = PDG_MODEL_GGM; P.ll_cap = 0;
+    // Large p: the in-kernel randomiser needs more shared memory per warp than the MH loop, so the loop's
+    // scratch triangle takes the difference and holds cliques well above 32 vertices (p = 500: 59) that
+    // would otherwise be factorised in the global scratch.
+    P.tri_extra = 0; P.ktri_run = 32;
+    if (!ctx->smem_state && !getenv("PDG_NO_TRI_EXTRA")) {
+        const RunSmem L0 = run_smem_layout(P.p, P.W, false, tri_bytes_for(0));
+        const RandSmem LR = rand_smem_layout(P.p, P.W);
+        int extra = ((LR.total - L0.total) / 16) * 16;
+        if (extra > 0) {
+            int k = 32;
+            while ((long long)(k + 1) * (k + 2) / 2 * 8 <= (long long)tri_bytes_for(0) + extra && k + 1 <= P.kbig) ++k;
+            P.tri_extra = extra; P.ktri_run = k;
+        }
+    }
     ctx->model_set = true;
     return memo_clear(ctx);                 // cached scores belong to the model that produced them
 }
@@ -403,7 +418,7 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
     CK(cudaStreamSynchronize(ctx->stream));       // the host arrays may go away after the call
     P.data_ld = (long long)ld; P.nrows = nrows; P.cell_alpha = cell_alpha;
     P.n_ktab = n_ktab; P.hist_cells = hist_cells;
-    P.model = PDG_MODEL_LOGLIN;
+    P.model = PDG_MODEL_LOGLIN; P.tri_extra = 0; P.ktri_run = 32;
     // few rows: a scan is cheap, so the light kernel (two CTAs per SM, 1024-cell tables) runs the chains
     ctx->light = nrows <= 8192;
     if (const char *v = getenv("PDG_LIGHT")) ctx->light = atoi(v) != 0;

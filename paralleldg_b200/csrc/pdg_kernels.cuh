@@ -55,6 +55,7 @@ struct PdgParams {
     double delta, nobs;
     double *big;                // [warp slot] packed triangles for cliques > 32
     int kbig;                   // largest clique the scratch supports
+    int tri_extra, ktri_run;    // MH kernel: bytes added to the warp's shared triangle and the largest clique it holds
     // log-linear
     const unsigned char *data;  // [p][nrows] level codes, column-major
     const int *levels;          // [p]
@@ -241,6 +242,7 @@ __host__ __device__ inline int tri_bytes_for(int ll_cap) { return ll_cap > 0 ? (
 struct HelpBox;
 struct WarpScratch {
     HelpBox *help;            // log-linear MH kernel: the CTA's scan-sharing mailbox (pdg_loglin.cuh), else null
+    int ktri;                 // largest clique the shared triangle tri32 holds (32 unless the MH kernel has room to spare)
     double *tri32;            // 528 doubles, or the log-linear count table (shared)
     short *idx;               // p + 1 entries (shared)
     double *big;              // global scratch for k > 32 (may be null)
@@ -282,11 +284,16 @@ __device__ __forceinline__ bool gather_ldl(const double *__restrict__ mat, int p
             if (lane <= i) a[tri(i, lane)] = __ldg(mat + (size_t)ri * p + mycol);
         }
     } else {
-        for (int i = lane; i < k; i += 32) {
+        // more than 32 vertices: lanes sweep the columns of one row after the other, so the loads of a
+        // row -- and, unrolled, of four rows -- are independent (a lane per ROW walked its columns one
+        // dependent L2 round trip at a time)
+#pragma unroll 4
+        for (int i = 0; i < k; ++i) {
             const double *row = mat + (size_t)idx[i] * p;
             double *dst = a + tri(i, 0);
-            for (int l = 0; l <= i; ++l) dst[l] = __ldg(row + idx[l]);
+            for (int l = lane; l <= i; l += 32) dst[l] = __ldg(row + idx[l]);
         }
+        __syncwarp();
     }
     double sS, ldv, lsc;
     return ldl_logdets(a, lane, k, 0, k, sS, logdet, ldv, lsc);
@@ -301,7 +308,7 @@ __device__ __forceinline__ int ggm_set_score(const PdgParams &P, const WarpScrat
     const int k = build_index_sorted<WMAX>(X, P.W, lane, ws.idx);
     if (k == 0) { score = 0.0; return 0; }
     double *a = ws.tri32;
-    if (k > 32) {
+    if (k > ws.ktri) {
         if (!ws.big || k > ws.kbig) return ERR_BIGCLIQUE;
         a = ws.big;
     }

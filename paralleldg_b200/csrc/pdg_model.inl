@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(32) k_init_logl(PdgParams P, int kind)
     unsigned char *s_first = smem + L.off_first;
     WarpScratch ws;
     ws.help = nullptr;
+    ws.ktri = 32;
     ws.tri32 = (double *)(smem + L.off_tri);
     ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(32) k_score_sets(PdgParams P, const u64 *bits,
     const int W = P.W, lane = threadIdx.x;
     WarpScratch ws;
     ws.help = nullptr;
+    ws.ktri = 32;
     LaneScratch ls;
     ws.tri32 = (double *)smem;
     ls.unused = 0;
@@ -198,7 +200,7 @@ int set_smem(pdg_ctx *ctx, F f, int bytes)
 template <int MODEL, int WMAX, bool SS, bool LIGHT, bool DIAG, bool SPEC>
 int launch_run_k(pdg_ctx *ctx, int kind, long long b, long long e, const PdgReplayDev &R, long long randomize)
 {
-    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap));
+    const RunSmem L = run_smem_layout(ctx->P.p, ctx->P.W, SS, tri_bytes_for(ctx->P.ll_cap) + ctx->P.tri_extra);
     const RandSmem LR = rand_smem_layout(ctx->P.p, ctx->P.W);
     // shared memory per chain: one warp region, or the two regions of a pair back to back; the in-kernel
     // randomiser may use all of it
@@ -392,6 +394,10 @@ extern "C" int pdg_debug_loglin_kh(unsigned long long *out)
 #endif
 
 #if defined(PDG_PHASE_TIMERS) && defined(PDG_TU_IS_GGM)
+extern "C" int pdg_debug_ggm_rz(unsigned long long *out)
+{
+    return cudaMemcpyFromSymbol(out, g_rz, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -2;
+}
 extern "C" int pdg_debug_ggm_kg(unsigned long long *out)
 {
     return cudaMemcpyFromSymbol(out, g_kg, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : -2;

@@ -217,6 +217,12 @@ __device__ __forceinline__ int mcs_cliques(const u64 *adj, u64 *K, u64 *sep, u64
     return S;
 }
 
+#ifdef PDG_PHASE_TIMERS
+static __device__ unsigned long long g_rz[8];     // developer probe: cycles of the randomiser's stages (adjacency, search, separators, relabel, derived)
+#define RZ(i) { const long long n_ = clock64(); if (lane == 0) atomicAdd(&g_rz[i], (unsigned long long)(n_ - rz_t)); rz_t = n_; }
+#else
+#define RZ(i)
+#endif
 // randomisation of ONE chain by ONE warp; `smem` = rand_smem_layout(p, W).total bytes of warp-private
 // shared memory.  Works on the global-memory state and rebuilds N and the CSR at the end.
 static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, long long chain, u32 iter,
@@ -245,6 +251,9 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
     int *E = P.edges + (size_t)chain * 2 * (p - 1);
     const u32 gchain = P.chain0 + (u32)chain, k0 = P.seed_lo, k1 = P.seed_hi;
 
+#ifdef PDG_PHASE_TIMERS
+    long long rz_t = clock64();
+#endif
     int S = 0;
     // Two codings of steps (a) and (b) with identical results: up to 128 vertices the gather /
     // shared-memory form is the shorter one, above it the scatter / register form (1.4 -> 1.0 ms
@@ -298,10 +307,11 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
         }
         __threadfence();          // fire-and-forget reductions: performed before any lane reads a row back
         __syncwarp();
-
+        RZ(0)
         S = mcs_cliques<8, true>(adj, K, sep, numbered, order, cliqueof, parent, p, W, lane);
     }
 
+    RZ(1)
     // per clique: which words are non-empty (W <= 8 -> one byte) and the separator size, in shared
     // memory, so that the per-separator scans below reject almost every clique without a global load
     for (int d = lane; d < S; d += 32) {
@@ -390,6 +400,7 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
         __syncwarp();
     }
     if (ne != (S > 0 ? S - 1 : 0)) { if (lane == 0) atomicOr(&P.err[chain], ERR_NUMERIC); }
+    RZ(2)
 
     // ---- (d) relabel + pad (junction_tree.py:36-64) ------------------------------------------
     for (int i = lane; i < p; i += 32) {
@@ -427,7 +438,12 @@ static __device__ __noinline__ void randomize_chain(RandArgs P, RandScratch Z, l
     }
     __syncwarp();
     __threadfence_block();
+    RZ(3)
     build_derived(P, chain, lane, (int *)(smem + L.off_deg32));
+    RZ(4)
+#ifdef PDG_PHASE_TIMERS
+    if (lane == 0) { atomicAdd(&g_rz[5], 1ull); atomicAdd(&g_rz[6], (unsigned long long)S); }
+#endif
 }
 
 #ifdef PDG_DEFINE_GLOBAL_KERNELS

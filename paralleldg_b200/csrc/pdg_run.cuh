@@ -170,7 +170,7 @@ template <bool SMEM_STATE>
 static __device__ __noinline__ void reload_chain_state(const PdgParams &P, unsigned char *smem, long long chain, int lane)
 {
     const int p = P.p, W = P.W;
-    const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
+    const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap) + P.tri_extra);
     unsigned short *s_off = (unsigned short *)(smem + L.off_csr_off);
     unsigned short *s_adj = (unsigned short *)(smem + L.off_csr_adj);
     for (int i = lane; i <= p; i += 32) s_off[i] = P.csr_off[(size_t)chain * (p + 1) + i];
@@ -237,7 +237,7 @@ k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin, long
     const long long chain = (long long)blockIdx.x * wpc + cw;
     if (chain >= P.n_chains) return;                       // (whole pairs leave; the barriers count live warps only)
     const int live_threads = 32 * (int)(((long long)(blockIdx.x + 1) * wpc <= P.n_chains) ? wpc : (P.n_chains - (long long)blockIdx.x * wpc));
-    const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap));
+    const RunSmem L = run_smem_layout(p, W, SMEM_STATE, tri_bytes_for(P.ll_cap) + P.tri_extra);
     // `smem_per_warp` bytes per CHAIN: one warp region (L.total, or the randomiser's layout if larger), or
     // the two regions of a pair back to back (the randomiser, run by the first warp while the second one
     // waits, may spread over both).  Chain state and pair mailbox sit in the first warp's region.
@@ -258,6 +258,7 @@ k_mh_run(const __grid_constant__ PdgParams P, int kind, long long it_begin, long
     const int bar_id = 1 + cw;
     WarpScratch ws;
     ws.help = HELP ? &s_help : nullptr;
+    ws.ktri = P.ktri_run;
     ws.tri32 = (double *)(smem + L.off_tri);
     ws.idx = (short *)(smem + L.off_idx);
     ws.kbig = P.kbig;

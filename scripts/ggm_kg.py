@@ -36,3 +36,8 @@ for k in range(1, 64):
 ph = ctx.work()["phase"]
 names = ["draw+sub(+randomise, barriers)", "scan", "movelist", "sets", "score", "delta+accept", "apply"]
 print("phase cycles/iter/chain: " + "  ".join("%s %.0f" % (nm, v / float(w["chains"] * w["M"])) for nm, v in zip(names, ph)))
+rz = (C.c_uint64 * 8)()
+if nat.lib().pdg_debug_ggm_rz(rz) == 0 and rz[5]:
+    calls = float(rz[5])
+    print("in-kernel randomiser, cycles per call: adjacency %.0f  search %.0f  separators+Pruefer %.0f  relabel %.0f  derived %.0f  (%.0f calls, %.1f cliques on average)" % (
+        rz[0] / calls, rz[1] / calls, rz[2] / calls, rz[3] / calls, rz[4] / calls, calls, rz[6] / calls))
