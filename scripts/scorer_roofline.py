@@ -44,14 +44,14 @@ def main():
     ceil = {k: nat.probe(k) for k in nat.PROBES}
     print(json.dumps({"machine_ceilings": ceil}), flush=True)
     rng = np.random.RandomState(0)
-    if which in ("all", "ggm"):
-        p, n = 500, 1000
+    if which in ("all", "ggm", "ggm_big"):
+        p, n = (500, 1000) if which != "ggm_big" else (300, 600)
         X, _ = datagen.ggm_ar_data(p, n, 500)
         sd = seqdist.GGMJTPosterior()
         sd.init_model(X, np.identity(p), 1.0, {})
         ctx = nat.Context(p, 1024, 1, rec_cap=0)
         engine.configure_model(ctx, sd)
-        for k in (8, 12, 16, 32, 48, 64, 96, 128, 160, 187):
+        for k in ((8, 12, 16, 32, 48, 64, 96, 128, 160, 187) if which != "ggm_big" else (128,)):
             N = 8192 if k <= 64 else 2048
             best = None
             for rep in range(3):
