@@ -318,3 +318,102 @@ def sample_trajectory_ggm(dataframe, n_samples, randomize=1000, D=None, delta=1.
     sd = seqdist.GGMJTPosterior()
     sd.init_model(X, D, delta, {})
     return sample_trajectory(n_samples, randomize, sd, **args)
+
+
+# ---- file output and the batch wrappers (mh_greenthomas.py:255-501) ------------------------------
+def graph_diff_trajectory_df(gtraj):
+    """benchpress format of a graph trajectory (mh_greenthomas.py:438-478): the star-graph preamble rows
+    (index -2, -1), the start graph at index 0 and one row per MCMC index at which the graph changed, with
+    the log target as score.  (As in the reference, the last two indices are not examined.)"""
+    import pandas as pd
+
+    def edge_string(edges):
+        return "[" + ";".join("%s-%s" % tuple(sorted(e)) for e in edges) + "]"
+    graphs = gtraj.trajectory
+    star = [(0, i) for i in range(1, graphs[0].order())]
+    rows = [(-2, edge_string(star), "[]", 0), (-1, "[]", edge_string(star), 0),
+            (0, edge_string(list(graphs[0].edges())), "[]", gtraj.logl[0])]
+    for i in range(1, len(graphs) - 2):
+        cur, prev = graphs[i], graphs[i - 1]
+        if cur is prev:
+            continue
+        e_cur = set(frozenset(e) for e in cur.edges())
+        e_prev = set(frozenset(e) for e in prev.edges())
+        if e_cur != e_prev:
+            rows.append((i, edge_string([tuple(e) for e in e_cur - e_prev]), edge_string([tuple(e) for e in e_prev - e_cur]),
+                         gtraj.logl[i]))
+    return pd.DataFrame(rows, columns=["index", "added", "removed", "score"])[["index", "added", "removed", "score"]]
+
+
+def write_traj_to_file(graph_trajectory, dirt, output_filename=None, output_format=None):
+    """mh_greenthomas.py:482-501"""
+    import datetime
+    import os
+    if not os.path.exists(dirt):
+        os.makedirs(dirt)
+    if output_format == 'benchpress':
+        filename = os.path.join(dirt, output_filename)
+        graph_diff_trajectory_df(graph_trajectory).to_csv(filename, sep=",", index=False)
+    else:
+        date = datetime.datetime.today().strftime('%Y%m%d%H%m%S')
+        filename = os.path.join(dirt, str(graph_trajectory) + "_" + date + ".json")
+        graph_trajectory.write_file(filename=filename)
+    print("wrote file: " + filename)
+    return filename
+
+
+def trajectory_to_file(n_samples, randomize, seqdist, dir=".", reseed=False, **args):
+    """mh_greenthomas.py:305-334"""
+    graph_trajectory = sample_trajectory(n_samples, randomize, seqdist, **args)
+    seed = args.get('seed', int(time.time()))
+    output_filename = args.get("output_filename") or 'graph_traj_' + str(seed) + '.csv'
+    write_traj_to_file(graph_trajectory, dirt=dir, output_filename=output_filename, output_format=args.get("output_format"))
+    return graph_trajectory
+
+
+def _ggm_sd(dataframe, D, delta):
+    X = np.asarray(dataframe, dtype=np.float64)
+    sd = seqdist.GGMJTPosterior()
+    sd.init_model(X, np.identity(X.shape[1]) if D is None else D, delta, {})
+    return sd
+
+
+def sample_trajectories_ggm_to_file(dataframe, n_samples, randomize=[1000], D=None, delta=1.0, reps=1,
+                                    output_directory=".", **args):
+    """mh_greenthomas.py:363-389: one trajectory per (repetition, interval, length), each written to file"""
+    out = []
+    for _ in range(reps):
+        for r in randomize:
+            for T in n_samples:
+                out.append(trajectory_to_file(T, r, _ggm_sd(dataframe, D, delta), dir=output_directory, **args))
+    return out
+
+
+def sample_trajectories_ggm_parallel(dataframe, n_samples, randomize=[1000], D=None, delta=1.0, reps=1, **args):
+    """mh_greenthomas.py:392-435.  The reference forks one process per setting; the settings run one after
+    the other here (they share the GPU scorer), and are written out when output_directory is given."""
+    out = []
+    directory = args.pop("output_directory", None)
+    for _ in range(reps):
+        for r in randomize:
+            for T in n_samples:
+                out.append(sample_trajectory(T, r, _ggm_sd(dataframe, D, delta), **args))
+    if directory is not None:
+        for t in out:
+            write_traj_to_file(t, directory)
+    return out
+
+
+def sample_trajectories_loglin_to_file(dataframe, n_samples, randomize=[1000], pseudo_obs=[1.0], reps=1,
+                                       output_directory=".", **args):
+    """mh_greenthomas.py:255-271"""
+    n_levels = np.array(dataframe.columns.get_level_values(1), dtype=int)
+    out = []
+    for _ in range(reps):
+        for r in randomize:
+            for T in n_samples:
+                for po in (pseudo_obs if isinstance(pseudo_obs, (list, tuple)) else [pseudo_obs]):
+                    sd = seqdist.LogLinearJTPosterior()
+                    sd.init_model(dataframe.to_numpy(), po, [list(range(int(l))) for l in n_levels], {})
+                    out.append(trajectory_to_file(T, r, sd, dir=output_directory, **args))
+    return out

@@ -210,3 +210,37 @@ def test_production_run_on_the_gpu_scorer_and_trajectory_output(tmp_path):
     assert abs(gt.log_target(t.seqdist, final) - t.logl[-1]) <= 1e-8 * abs(t.logl[-1])
     heat = np.asarray(t.empirical_distribution(500).heatmap())
     assert heat.shape == (10, 10) and heat.max() <= 1.0 + 1e-12
+
+
+def test_benchpress_rows_of_a_graph_trajectory():
+    """graph_diff_trajectory_df (mh_greenthomas.py:438-478) on a hand-made trajectory"""
+    from paralleldg_b200 import mh_greenthomas as gt
+    from paralleldg_b200.graph import trajectory as tj
+    g0 = nx.Graph(); g0.add_nodes_from(range(4))
+    g1 = g0.copy(); g1.add_edge(0, 1)
+    g2 = g1.copy(); g2.add_edge(2, 3); g2.remove_edge(0, 1)
+    t = tj.Trajectory()
+    t.set_trajectory([g0, g0, g1, g1, g2, g2, g2, g2])
+    t.logl = [0.5, 0.5, 1.5, 1.5, 2.5, 2.5, 2.5, 2.5]
+    df = gt.graph_diff_trajectory_df(t)
+    assert list(df["index"]) == [-2, -1, 0, 2, 4]
+    assert list(df["added"]) == ["[0-1;0-2;0-3]", "[]", "[]", "[0-1]", "[2-3]"]
+    assert list(df["removed"]) == ["[]", "[0-1;0-2;0-3]", "[]", "[]", "[0-1]"]
+    assert list(df["score"]) == [0, 0, 0.5, 1.5, 2.5]
+
+
+@pytest.mark.gpu
+def test_mh_ggm_sample_cli(tmp_path):
+    import subprocess
+    import sys
+    import pandas as pd
+    from paralleldg_b200 import datagen
+    X, _ = datagen.ggm_ar_data(8, 60, seed=2)
+    f = os.path.join(str(tmp_path), "d.csv")
+    pd.DataFrame(X).to_csv(f, index=False)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bin", "mh_ggm_sample"), "-M", "400", "-r", "50", "-f", f, "-s", "3",
+                        "-o", str(tmp_path), "-t", "benchpress", "-F", "gt.csv"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    df = pd.read_csv(os.path.join(str(tmp_path), "gt.csv"))
+    assert list(df.columns) == ["index", "added", "removed", "score"] and list(df["index"][:3]) == [-2, -1, 0]
