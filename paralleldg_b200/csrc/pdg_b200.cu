@@ -946,4 +946,16 @@ int pdg_get_work(pdg_ctx *ctx, int64_t work[16])
     return PDG_OK;
 }
 
+#ifdef PDG_PHASE_TIMERS
+/* developer probe (PDG_PHASE_TIMERS builds only): the raw per-slot work counters, [2 * n_chains][16] */
+int pdg_debug_work_per_chain(pdg_ctx *ctx, void *out)
+{
+    if (!ctx || !out) return PDG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->P.work, (size_t)ctx->P.n_chains * 2 * 16 * 8, cudaMemcpyDeviceToHost));
+    return PDG_OK;
+}
+#endif
+
 }  // extern "C"

@@ -22,7 +22,12 @@ struct LoglinArgs {
 };
 template <int WMAX> struct KeyW { u64 w[WMAX]; };
 #ifdef PDG_PHASE_TIMERS
-static __device__ unsigned long long g_kh[2][32];      // developer probe: scans and cycles by set size
+static __device__ unsigned long long g_kh[2][32];
+static __device__ unsigned long long g_sp[8];        // developer probe: cycles of the hashed path's stages
+#define SPT(i) { const long long n_ = clock64(); if (lane == 0) atomicAdd(&g_sp[i], (unsigned long long)(n_ - sp_t)); sp_t = n_; }      // developer probe: scans and cycles by set size
+#endif
+#ifndef PDG_PHASE_TIMERS
+#define SPT(i)
 #endif
 struct ScoreRes { double score; int err; };
 
@@ -89,6 +94,8 @@ __device__ __forceinline__ void loglin_count_dense(const unsigned char *D, long 
     // a, b: this row's codeA / codeB (MODE 1) or the code and nothing (MODE 0, 2)
     auto count1 = [&](unsigned int a, unsigned int b) {
         if (GLB) {
+            // (merging the lanes of one cell with match.any before the reduction was measured: the match costs
+            // more per row than the serialised reductions on a hot cell save -- 66.9 -> 59.5 M proposals/s)
             if (MODE == 1) atomicAdd(&q.hist[a * q.mulA + b], 1u); else atomicAdd(&q.hist[a], 1u);
         } else {
             if (MODE == 1) ll_red_shared(a * q.mulA + (b * q.mulB + q.sbase)); else ll_red_shared(a * q.mulA + q.sbase);
@@ -450,41 +457,84 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     unsigned int *hc = S.hcnt + (size_t)s * S.hslots, *cc = S.cc + (size_t)s * (size_t)(n + 2);
     int *list = S.list + (size_t)s * (size_t)(n + 1);          // list[0] = 0 on entry
     const u32 hmask = (u32)S.hslots - 1u;
-    // Keys: every lane builds the mixed-radix codes of 16 consecutive rows from one 16-byte load per column
-    // (a warp pass covers 512 rows), four columns' loads in flight; missing columns of the last group read
-    // the zero column with multiplier 1, as in the dense pass.  (One row per lane and one byte per load, with
-    // the multiply-add chain waiting for every load in turn, took 14 ms per 17-column scan.)
+    // Keys.  The sorted columns are split greedily into groups of <= 256 cells each (<= 8 groups: the code fits
+    // 62 bits); every lane covers 16 consecutive rows with one 16-byte load per column, and a group's code
+    // is built with the dense pass's packed arithmetic -- four rows per 32-bit multiply-add -- into one
+    // byte-packed accumulator per four rows; only the few group codes of a row are then combined in 64 bits.
+    // Groups are padded to four column slots with the zero column and multiplier 1.  (One row per lane, one
+    // byte per load and a 64-bit multiply-add per column and row took 14 ms per 17-column scan; 64-bit
+    // multiply-adds over 16 rows per load still 2.2 ms.)
     // Insertion: cells of a clique's table are concentrated, so lanes holding the same key are merged first
     // (match.any: one leader adds the group's count), and a slot that already holds the key is found by a
     // plain L2 read -- eight in flight -- with the count added fire-and-forget; only a key's first insertion
     // waits for a compare-and-swap and records its slot in the list.
+#ifdef PDG_PHASE_TIMERS
+    long long sp_t = clock64();
+#endif
+    unsigned int *sh = (unsigned int *)ws.tri32;          // the count table is idle on this path: slot lists live there
+    unsigned int *slot_mul = sh, *slot_col = sh + 64, *grp_lo = sh + 128, *grp_cells = sh + 144;   // [64] [64] [9] [8]
+    int G = 0;
+    if (lane == 0) {
+        int nslot = 0, g = 0;
+        unsigned int prod = 1u;
+        grp_lo[0] = 0u;
+        for (int j = 0; j < k; ++j) {
+            const unsigned int gcol = (unsigned int)ws.idx[j], Lj = (unsigned int)P.levels[gcol];
+            if (prod * Lj > 256u) {                            // close the group: pad to four slots
+                while (nslot & 3) { slot_mul[nslot] = 1u; slot_col[nslot] = (unsigned int)P.zero_col; ++nslot; }
+                grp_cells[g] = prod; ++g; grp_lo[g] = (unsigned int)nslot; prod = 1u;
+            }
+            slot_mul[nslot] = Lj; slot_col[nslot] = gcol; ++nslot; prod *= Lj;
+        }
+        while (nslot & 3) { slot_mul[nslot] = 1u; slot_col[nslot] = (unsigned int)P.zero_col; ++nslot; }
+        grp_cells[g] = prod; ++g; grp_lo[g] = (unsigned int)nslot;
+        G = g;
+    }
+    G = __shfl_sync(PDG_FULL, G, 0);
+    __syncwarp();
+    if (G > 8) { if (lane == 0) atomicExch(&S.lock[s], 0); res.err = ERR_BIGCLIQUE; return res; }
+    // a lane that leads the same key again and again (the table's heaviest cell, as a rule) keeps that cell's
+    // count in registers and adds it once: repeated reductions on one address were most of the insertion time
+    u64 pend_key = 0ull;
+    u32 pend_h = 0u, pend_cnt = 0u;
     for (long long base = 0; base < n; base += 512) {
         const long long r0 = base + lane * 16;
+        unsigned int c[8][4];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) c[g][w] = 0u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (g < G) {
+                const int lo = (int)grp_lo[g], hi = (int)grp_lo[g + 1];
+                for (int s0 = lo; s0 < hi; s0 += 4) {
+                    uint4 x[4];
+                    unsigned int L4[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        L4[jj] = slot_mul[s0 + jj];
+                        x[jj] = __ldg((const uint4 *)(D + (size_t)slot_col[s0 + jj] * (size_t)P.ld + r0));
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        c[g][0] = c[g][0] * L4[jj] + x[jj].x; c[g][1] = c[g][1] * L4[jj] + x[jj].y;
+                        c[g][2] = c[g][2] * L4[jj] + x[jj].z; c[g][3] = c[g][3] * L4[jj] + x[jj].w;
+                    }
+                }
+            }
+        }
+        SPT(0)
         u64 keys[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) keys[i] = 0ull;
-        uint4 x[4], xn[4];
-        u64 Lc[4], Ln[4];
-        auto load_group = [&](int j0, uint4 (&xx)[4], u64 (&LL)[4]) {
+        for (int i = 0; i < 16; ++i) keys[i] = (u64)((c[0][i >> 2] >> (8 * (i & 3))) & 0xffu);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = j0 + jj;
-                const int g = j < k ? (int)ws.idx[j] : P.zero_col;
-                LL[jj] = j < k ? (u64)__ldg(&P.levels[g]) : 1ull;
-                xx[jj] = __ldg((const uint4 *)(D + (size_t)g * (size_t)P.ld + r0));
+        for (int g = 1; g < 8; ++g) {
+            if (g < G) {
+                const u64 Kg = (u64)grp_cells[g];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) keys[i] = keys[i] * Kg + (u64)((c[g][i >> 2] >> (8 * (i & 3))) & 0xffu);
             }
-        };
-        load_group(0, x, Lc);
-        for (int j0 = 0; j0 < k; j0 += 4) {
-            if (j0 + 4 < k) load_group(j0 + 4, xn, Ln);          // the next group's loads fly while this one is folded in
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const unsigned int w4[4] = {x[jj].x, x[jj].y, x[jj].z, x[jj].w};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) keys[i] = keys[i] * Lc[jj] + (u64)((w4[i >> 2] >> (8 * (i & 3))) & 0xffu);
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) { x[jj] = xn[jj]; Lc[jj] = Ln[jj]; }
         }
 #pragma unroll
         for (int i0 = 0; i0 < 16; i0 += 8) {
@@ -497,26 +547,65 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
                 const u32 m = __match_any_sync(PDG_FULL, key[u]);
                 lead[u] = key[u] != 0ull && (int)(__ffs((int)m) - 1) == lane;
                 cnt[u] = (u32)__popc(m);
-                hh[u] = (u32)mix64(key[u]) & hmask;
-                cur[u] = lead[u] ? __ldcg(&hk[hh[u]]) : 0ull;
+                hh[u] = (u32)((key[u] * 0x9E3779B97F4A7C15ull) >> 32) & hmask;      // (Fibonacci hashing: one multiply)
+                if (lead[u] && key[u] == pend_key) { cur[u] = key[u]; hh[u] = pend_h; }      // its slot is known
+                else cur[u] = lead[u] ? __ldcg(&hk[hh[u]]) : 0ull;
+            }
+            // second wave: the leaders that saw an empty slot try to take it -- all compare-and-swaps of the
+            // batch in flight together
+            u64 old[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) old[u] = (lead[u] && cur[u] == 0ull) ? atomicCAS(&hk[hh[u]], 0ull, key[u]) : cur[u];
+            int nfresh = 0;
+            u32 freshm = 0u, hitm = 0u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool fresh = lead[u] && cur[u] == 0ull && old[u] == 0ull;
+                const bool hit = lead[u] && (fresh || old[u] == key[u]);
+                freshm |= (u32)fresh << u; hitm |= (u32)hit << u;
+                nfresh += fresh ? 1 : 0;
+            }
+            // new cells are listed with ONE counter update per batch (warp prefix over the lanes' counts)
+            int incl = nfresh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(PDG_FULL, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(PDG_FULL, incl, 31);
+            if (total) {
+                int lbase = 0;
+                if (lane == 31) lbase = atomicAdd(&list[0], total);
+                lbase = __shfl_sync(PDG_FULL, lbase, 31) + incl - nfresh;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if ((freshm >> u) & 1u) list[1 + lbase++] = (int)hh[u];
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (!lead[u]) continue;
-                u32 h = hh[u];
-                u64 c = cur[u];
+                if (!((hitm >> u) & 1u)) continue;
+                if (key[u] == pend_key) pend_cnt += cnt[u];
+                else {
+                    if (pend_cnt) atomicAdd(&hc[pend_h], pend_cnt);
+                    pend_key = key[u]; pend_h = hh[u]; pend_cnt = cnt[u];
+                }
+            }
+            // the rest met another key in their slot: linear probing, one at a time (rare at this load factor)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (!lead[u] || ((hitm >> u) & 1u)) continue;
+                u32 h = (hh[u] + 1) & hmask;
+                u64 c2 = __ldcg(&hk[h]);
                 for (;;) {
-                    if (c == 0ull) {
-                        c = atomicCAS(&hk[h], 0ull, key[u]);
-                        if (c == 0ull) list[1 + atomicAdd(&list[0], 1)] = (int)h;      // a new cell: remember its slot
+                    if (c2 == 0ull) {
+                        c2 = atomicCAS(&hk[h], 0ull, key[u]);
+                        if (c2 == 0ull) list[1 + atomicAdd(&list[0], 1)] = (int)h;      // a new cell: remember its slot
                     }
-                    if (c == 0ull || c == key[u]) { atomicAdd(&hc[h], cnt[u]); break; }
+                    if (c2 == 0ull || c2 == key[u]) { atomicAdd(&hc[h], cnt[u]); break; }
                     h = (h + 1) & hmask;
-                    c = __ldcg(&hk[h]);
+                    c2 = __ldcg(&hk[h]);
                 }
             }
         }
+        SPT(1)
     }
+    if (pend_cnt) atomicAdd(&hc[pend_h], pend_cnt);
     __threadfence();
     __syncwarp();
     // the occupied slots come off the list (a few thousand cells), not off a pass over the whole table
@@ -540,14 +629,15 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     maxc = __reduce_max_sync(PDG_FULL, maxc);
     __threadfence();
     __syncwarp();
+    SPT(2)
     if (lane == 0) list[0] = 0;
-    // count-of-counts in ascending count order (order-free sum), four loads in flight per lane
-    for (unsigned int c0 = 1; c0 <= maxc; c0 += 128) {
-        unsigned int mx[4];
+    // count-of-counts in ascending count order (order-free sum), eight loads in flight per lane
+    for (unsigned int c0 = 1; c0 <= maxc; c0 += 256) {
+        unsigned int mx[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const unsigned int c = c0 + 32 * u + lane; mx[u] = c <= maxc ? __ldcg(&cc[c]) : 0u; }
+        for (int u = 0; u < 8; ++u) { const unsigned int c = c0 + 32 * u + lane; mx[u] = c <= maxc ? __ldcg(&cc[c]) : 0u; }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const unsigned int c = c0 + 32 * u + lane;
             if (mx[u]) {
                 acc += (double)mx[u] * (LG ? LG[c] : (lgamma((double)c + alpha) - lga));
@@ -557,6 +647,10 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     }
     __threadfence();
     __syncwarp();
+    SPT(3)
+#ifdef PDG_PHASE_TIMERS
+    if (lane == 0) { atomicAdd(&g_sp[4], 1ull); atomicAdd(&g_sp[5], (unsigned long long)ncell); atomicAdd(&g_sp[6], (unsigned long long)maxc); }
+#endif
     if (lane == 0) atomicExch(&S.lock[s], 0);
     score = warp_sum(acc) - constK;
     res.score = score;

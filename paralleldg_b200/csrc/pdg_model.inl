@@ -387,6 +387,10 @@ int launch_score_m(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_
 
 #if defined(PDG_PHASE_TIMERS) && defined(PDG_TU_IS_LOGLIN)
 // developer probe (PDG_PHASE_TIMERS builds only): scans and cycles by set size, see loglin_scan
+extern "C" int pdg_debug_loglin_sp(unsigned long long *out)
+{
+    return cudaMemcpyFromSymbol(out, g_sp, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -2;
+}
 extern "C" int pdg_debug_loglin_kh(unsigned long long *out)
 {
     return cudaMemcpyFromSymbol(out, g_kh, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -2;

@@ -30,3 +30,9 @@ for k in (12, 16, 17, 18, 20):
             torch.cuda.synchronize(); best = min(best, time.perf_counter() - t)
         distinct = len(np.unique(data[:, sets[0]], axis=0))
         print("k=%d sets=%d  %.3f ms per call  (distinct cells of the first set: %d)" % (k, N, best * 1e3, distinct))
+import ctypes as C
+sp = (C.c_uint64 * 8)()
+if hasattr(nat.lib(), "pdg_debug_loglin_sp") and nat.lib().pdg_debug_loglin_sp(sp) == 0 and sp[4]:
+    n_ = float(sp[4])
+    print("hashed path, cycles per scan: keys %.0f  insert %.0f  list pass %.0f  count-of-counts pass %.0f  (cells %.0f, largest count %.0f)" % (
+        sp[0] / n_, sp[1] / n_, sp[2] / n_, sp[3] / n_, sp[5] / n_, sp[6] / n_))
