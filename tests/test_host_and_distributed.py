@@ -127,12 +127,16 @@ def _worker(rank, world, port, q):
     b.bits = np.full((tot, 2, 1), rank + 1, np.uint64)
     b.final_edges = np.full((count, 2, 2), rank, np.int32)
     b.final_bits = np.full((count, 3, 1), rank, np.uint64)
+    b.edge_ess = np.arange(first, first + count, dtype=np.float64) * 0.5           # per-chain device post-processing results
+    b.edge_ess_edges = np.arange(first, first + count, dtype=np.int32)
+    b.sizes = np.full((count, 4), rank, np.int32)
     tallies = np.full((3, 3), rank + 1, np.int64)
     t, nprop, nacc = pd_dist.allreduce_tallies(tallies, b.n_proposals, b.n_accepted)
     g = pd_dist.gather_batches(b)          # sized all_gather_into_tensor: every rank gets everything
     q.put((rank, t.tolist(), nprop, nacc, g["n_chains"], g["offsets"].tolist(), g["records"]["i"].tolist(),
            g["n_proposals"].tolist(), g["records"]["node"].tolist(), g["bits"][:, 0, 0].tolist(),
-           g["logl"][:, 0].tolist(), g["final_edges"][:, 0, 0].tolist(), g["chains_per_rank"]))
+           g["logl"][:, 0].tolist(), g["final_edges"][:, 0, 0].tolist(), g["chains_per_rank"],
+           g["edge_ess"].tolist(), g["edge_ess_edges"].tolist(), g["sizes"][:, 0].tolist()))
     dist.destroy_process_group()
 
 
@@ -152,7 +156,8 @@ def test_world_size_2_reduction_and_gather_over_gloo():
         assert p_.exitcode == 0
     assert sorted(o[0] for o in outs) == [0, 1]
     for out in outs:
-        _, t, nprop, nacc, nch, offs, rec_i, props, nodes, bits, logl, fe, per_rank = out
+        _, t, nprop, nacc, nch, offs, rec_i, props, nodes, bits, logl, fe, per_rank, ess, ess_n, sizes = out
+        assert ess == [0.0, 0.5, 1.0, 1.5, 2.0] and ess_n == [0, 1, 2, 3, 4] and sizes == [0, 0, 0, 1, 1]
         assert t == [[3, 3, 3]] * 3
         assert nprop == sum(range(5)) + 50 and nacc == sum(range(5))
         assert nch == 5 and props == [10, 11, 12, 13, 14] and per_rank == [3, 2]
