@@ -472,6 +472,7 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
         res.score = score;
 #ifdef PDG_PHASE_TIMERS
         if (lane == 0) { atomicAdd(&g_kh[0][k < 31 ? k : 31], 1ull); atomicAdd(&g_kh[1][k < 31 ? k : 31], (unsigned long long)(clock64() - kh_t0)); }
+        if (lane == 0 && k >= 13) atomicAdd(&P.work[(size_t)slot * 16 + 15], (unsigned long long)(clock64() - kh_t0));    // per chain: cycles in scans of 13+ columns
 #endif
         return res;
     }
@@ -499,12 +500,12 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     // Groups are padded to four column slots with the zero column and multiplier 1.  (One row per lane, one
     // byte per load and a 64-bit multiply-add per column and row took 14 ms per 17-column scan; 64-bit
     // multiply-adds over 16 rows per load still 2.2 ms.)
-    // Insertion: cells of a clique's table are concentrated, so lanes holding the same key are merged first
-    // (match.any: one leader adds the group's count), and a slot that already holds the key is found by a
-    // plain L2 read -- eight in flight -- with the count added fire-and-forget; only a key's first insertion
-    // waits for a compare-and-swap and records its slot in the list.
+    // Insertion: a slot that already holds the key is found by a plain L2 read -- eight in flight -- with the
+    // count added fire-and-forget; only a key's first insertion waits for a compare-and-swap and records its
+    // slot in the list.
 #ifdef PDG_PHASE_TIMERS
     long long sp_t = clock64();
+    if (lane == 0) atomicAdd(&g_sp[7], (unsigned long long)(sp_t - kh_t0));      // wait for a pool
 #endif
     unsigned int *sh = (unsigned int *)ws.tri32;          // the count table is idle on this path: slot lists live there
     unsigned int *slot_mul = sh, *slot_col = sh + 64, *grp_lo = sh + 128, *grp_cells = sh + 144;   // [64] [64] [9] [8]
@@ -543,18 +544,20 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
         for (int g = 0; g < 8; ++g) {
             if (g < G) {
                 const int lo = (int)grp_lo[g], hi = (int)grp_lo[g + 1];
-                for (int s0 = lo; s0 < hi; s0 += 4) {
-                    uint4 x[4];
-                    unsigned int L4[4];
+                // (a group of binary columns is eight slots: all of its loads are in flight together)
+                for (int s0 = lo; s0 < hi; s0 += 8) {
+                    uint4 x[8];
+                    unsigned int L8[8];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        L4[jj] = slot_mul[s0 + jj];
-                        x[jj] = __ldg((const uint4 *)(D + (size_t)slot_col[s0 + jj] * (size_t)P.ld + r0));
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const bool in = s0 + jj < hi;
+                        L8[jj] = in ? slot_mul[s0 + jj] : 1u;
+                        x[jj] = in ? __ldg((const uint4 *)(D + (size_t)slot_col[s0 + jj] * (size_t)P.ld + r0)) : make_uint4(0u, 0u, 0u, 0u);
                     }
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        c[g][0] = c[g][0] * L4[jj] + x[jj].x; c[g][1] = c[g][1] * L4[jj] + x[jj].y;
-                        c[g][2] = c[g][2] * L4[jj] + x[jj].z; c[g][3] = c[g][3] * L4[jj] + x[jj].w;
+                    for (int jj = 0; jj < 8; ++jj) {
+                        c[g][0] = c[g][0] * L8[jj] + x[jj].x; c[g][1] = c[g][1] * L8[jj] + x[jj].y;
+                        c[g][2] = c[g][2] * L8[jj] + x[jj].z; c[g][3] = c[g][3] * L8[jj] + x[jj].w;
                     }
                 }
             }
@@ -579,9 +582,12 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 key[u] = (r0 + i0 + u < n) ? keys[i0 + u] + 1ull : 0ull;      // 0: no row
-                const u32 m = __match_any_sync(PDG_FULL, key[u]);
-                lead[u] = key[u] != 0ull && (int)(__ffs((int)m) - 1) == lane;
-                cnt[u] = (u32)__popc(m);
+                // (every row is its own leader: merging the lanes of one key with match.any first cost 4 400 cycles
+                // per match in the sampler -- 13.8 M of a 16.6 M-cycle scan -- and the tables of real cliques hold
+                // thousands of cells, the largest a few per cent of the rows; lanes that race for an empty slot with
+                // the same key all see it taken by that key, and only the winner lists the slot)
+                lead[u] = key[u] != 0ull;
+                cnt[u] = 1u;
                 hh[u] = (u32)((key[u] * 0x9E3779B97F4A7C15ull) >> 32) & hmask;      // (Fibonacci hashing: one multiply)
                 if (lead[u] && key[u] == pend_key) { cur[u] = key[u]; hh[u] = pend_h; }      // its slot is known
                 else cur[u] = lead[u] ? __ldcg(&hk[hh[u]]) : 0ull;
@@ -691,6 +697,7 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     res.score = score;
 #ifdef PDG_PHASE_TIMERS
     if (lane == 0) { atomicAdd(&g_kh[0][k < 31 ? k : 31], 1ull); atomicAdd(&g_kh[1][k < 31 ? k : 31], (unsigned long long)(clock64() - kh_t0)); }
+    if (lane == 0) atomicAdd(&P.work[(size_t)slot * 16 + 15], (unsigned long long)(clock64() - kh_t0));
 #endif
     return res;
 }

@@ -16,7 +16,8 @@ w = bench.WORKLOADS[name]
 inp, _ = bench.build_inputs(w)
 sd, sdg = bench.product_objects(w, inp)
 Cn = w["chains"]
-ctx = engine.make_context(sd, sdg, Cn, w["M"], seed=bench.SEED, rec_cap=w["M"])
+ctx = engine.make_context(sd, sdg, Cn, w["M"], seed=bench.SEED + int(os.environ.get("SEED_OFF", "0")),
+                          chain0=int(os.environ.get("CHAIN0", "0")), rec_cap=w["M"])
 ctx.set_cliques(None)
 ctx.randomize(0)
 ctx.enable_timing(True)
@@ -41,9 +42,11 @@ if out[Cn:, 2].any() and not out[1::2, 8:15].any():
     pass
 print("sets evaluated per chain: mean %.0f, slowest 1 %%: %.0f" % (ev.mean() if ev.sum() else 0, ev[order[-max(1, Cn // 100):]].mean() if ev.sum() else 0))
 print("slowest chains: time ms, sets evaluated, mean set size, sets on the hashed-cell path, score share")
+big = out[:Cn, 15].astype(np.float64) / 1.965e6        # ms in scans of 13+ columns (dense global tables and hashed cells)
+print("ms in scans of 13+ columns per chain: mean %.1f, slowest 1 %%: %.1f" % (big.mean(), big[order[-max(1, Cn // 100):]].mean()))
 byt = out[:Cn, 0].astype(np.float64)
 hashed = out[:Cn, 6].astype(np.float64)
 nrows = float(w.get("n", 1))
 for c in order[-8:][::-1]:
     mk = (byt[c] / nrows / ev[c]) if (w["model"] == "loglin" and ev[c]) else float("nan")
-    print("  chain %4d  %.1f ms  %5d sets  mean k %.2f  hashed %3d  score %.2f" % (c, tot[c], ev[c], mk, hashed[c], ph[c, 4] / ph[c].sum()))
+    print("  chain %4d  %.1f ms  %5d sets  mean k %.2f  hashed %3d  score %.2f  13+ columns %.1f ms" % (c, tot[c], ev[c], mk, hashed[c], ph[c, 4] / ph[c].sum(), big[c]))
