@@ -393,14 +393,14 @@ int pdg_set_model_loglin(pdg_ctx *ctx, const void *data, const void *levels, int
         CK(own((size_t)sp.nsp * hs * 8, &d_hk));
         CK(own((size_t)sp.nsp * hs * 4, &d_hc));
         CK(own((size_t)sp.nsp * (size_t)(nrows + 2) * 4, &d_cc));
-        CK(own((size_t)sp.nsp * (size_t)(nrows + 1) * 4, &d_list));
+        CK(own((size_t)sp.nsp * (size_t)(nrows + 512) * 4, &d_list));
         CK(cudaMemsetAsync(d_data, 0, data_bytes, ctx->stream));
         CK(cudaMemsetAsync(d_hist, 0, (size_t)2 * P.n_chains * hist_cells * 4, ctx->stream));
         CK(cudaMemsetAsync(d_lock, 0, (size_t)sp.nsp * 4, ctx->stream));
         CK(cudaMemsetAsync(d_hk, 0, (size_t)sp.nsp * hs * 8, ctx->stream));
         CK(cudaMemsetAsync(d_hc, 0, (size_t)sp.nsp * hs * 4, ctx->stream));
         CK(cudaMemsetAsync(d_cc, 0, (size_t)sp.nsp * (size_t)(nrows + 2) * 4, ctx->stream));
-        CK(cudaMemsetAsync(d_list, 0, (size_t)sp.nsp * (size_t)(nrows + 1) * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_list, 0, (size_t)sp.nsp * (size_t)(nrows + 512) * 4, ctx->stream));
         P.data = (const unsigned char *)d_data; P.levels = (const int *)d_lv;
         P.ktab = (const double *)d_k; P.alphatab = (const double *)d_a; P.lgtab = (const double *)d_lg;
         P.hist = (unsigned int *)d_hist;

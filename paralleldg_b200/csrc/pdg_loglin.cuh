@@ -23,7 +23,7 @@ struct LoglinArgs {
 template <int WMAX> struct KeyW { u64 w[WMAX]; };
 #ifdef PDG_PHASE_TIMERS
 static __device__ unsigned long long g_kh[2][32];
-static __device__ unsigned long long g_sp[8];        // developer probe: cycles of the hashed path's stages
+static __device__ unsigned long long g_sp[16];       // developer probe: cycles of the hashed path's stages
 #define SPT(i) { const long long n_ = clock64(); if (lane == 0) atomicAdd(&g_sp[i], (unsigned long long)(n_ - sp_t)); sp_t = n_; }      // developer probe: scans and cycles by set size
 #endif
 #ifndef PDG_PHASE_TIMERS
@@ -491,7 +491,9 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     s = __shfl_sync(PDG_FULL, s, 0);
     u64 *hk = S.hkeys + (size_t)s * S.hslots;
     unsigned int *hc = S.hcnt + (size_t)s * S.hslots, *cc = S.cc + (size_t)s * (size_t)(n + 2);
-    int *list = S.list + (size_t)s * (size_t)(n + 1);          // list[0] = 0 on entry
+    // slots taken by this scan, one list per lane (a lane meets at most its own rows: 16 per 512-row block)
+    int *mylist = S.list + (size_t)s * (size_t)(n + 512) + (size_t)lane * (size_t)(16 * ((n + 511) / 512));
+    int nlist = 0;
     const u32 hmask = (u32)S.hslots - 1u;
     // Keys.  The sorted columns are split greedily into groups of <= 256 cells each (<= 8 groups: the code fits
     // 62 bits); every lane covers 16 consecutive rows with one 16-byte load per column, and a group's code
@@ -533,115 +535,81 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     // count in registers and adds it once: repeated reductions on one address were most of the insertion time
     u64 pend_key = 0ull;
     u32 pend_h = 0u, pend_cnt = 0u;
+    // The key-building part is rolled over the column groups (the fully unrolled form of the loop body was
+    // 28 KB of straight-line code next to the MH loop of the SM's other warps).
     for (long long base = 0; base < n; base += 512) {
         const long long r0 = base + lane * 16;
-        unsigned int c[8][4];
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-#pragma unroll
-            for (int w = 0; w < 4; ++w) c[g][w] = 0u;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (g < G) {
-                const int lo = (int)grp_lo[g], hi = (int)grp_lo[g + 1];
-                // (a group of binary columns is eight slots: all of its loads are in flight together)
-                for (int s0 = lo; s0 < hi; s0 += 8) {
-                    uint4 x[8];
-                    unsigned int L8[8];
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const bool in = s0 + jj < hi;
-                        L8[jj] = in ? slot_mul[s0 + jj] : 1u;
-                        x[jj] = in ? __ldg((const uint4 *)(D + (size_t)slot_col[s0 + jj] * (size_t)P.ld + r0)) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        c[g][0] = c[g][0] * L8[jj] + x[jj].x; c[g][1] = c[g][1] * L8[jj] + x[jj].y;
-                        c[g][2] = c[g][2] * L8[jj] + x[jj].z; c[g][3] = c[g][3] * L8[jj] + x[jj].w;
-                    }
-                }
-            }
-        }
-        SPT(0)
         u64 keys[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) keys[i] = (u64)((c[0][i >> 2] >> (8 * (i & 3))) & 0xffu);
+        for (int i = 0; i < 16; ++i) keys[i] = 0ull;
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            unsigned int c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+            const int lo = (int)grp_lo[g], hi = (int)grp_lo[g + 1];
+            // (a group of binary columns is eight slots: all of its loads are in flight together)
+#pragma unroll 1
+            for (int s0 = lo; s0 < hi; s0 += 8) {
+                uint4 x[8];
+                unsigned int L8[8];
 #pragma unroll
-        for (int g = 1; g < 8; ++g) {
-            if (g < G) {
-                const u64 Kg = (u64)grp_cells[g];
+                for (int jj = 0; jj < 8; ++jj) {
+                    const bool in = s0 + jj < hi;
+                    L8[jj] = in ? slot_mul[s0 + jj] : 1u;
+                    x[jj] = in ? __ldg((const uint4 *)(D + (size_t)slot_col[s0 + jj] * (size_t)P.ld + r0)) : make_uint4(0u, 0u, 0u, 0u);
+                }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) keys[i] = keys[i] * Kg + (u64)((c[g][i >> 2] >> (8 * (i & 3))) & 0xffu);
+                for (int jj = 0; jj < 8; ++jj) {
+                    c0 = c0 * L8[jj] + x[jj].x; c1 = c1 * L8[jj] + x[jj].y;
+                    c2 = c2 * L8[jj] + x[jj].z; c3 = c3 * L8[jj] + x[jj].w;
+                }
             }
+            const u64 Kg = (u64)grp_cells[g];            // (keys are 0 before the first group)
+            const unsigned int cw[4] = {c0, c1, c2, c3};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) keys[i] = keys[i] * Kg + (u64)((cw[i >> 2] >> (8 * (i & 3))) & 0xffu);
+        }
+        SPT(0)
+        // All sixteen rows of the lane in ONE wave of compare-and-swaps: an empty slot is taken (a new cell: the
+        // lane notes the slot in its own list), a slot holding the key is a hit, anything else walks on.  The
+        // tables of real cliques hold thousands of thinly filled cells, so nearly every batch of rows opens new
+        // cells and meets an occupied home slot somewhere; with a read before the compare-and-swap, a shared
+        // list counter and one probe at a time a batch was six dependent L2 round trips (12.4 M cycles a scan).
+        u32 hh[16];
+        u64 old[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            keys[u] = (r0 + u < n) ? keys[u] + 1ull : 0ull;                       // 0: no row
+            hh[u] = (u32)((keys[u] * 0x9E3779B97F4A7C15ull) >> 32) & hmask;      // (Fibonacci hashing: one multiply)
         }
 #pragma unroll
-        for (int i0 = 0; i0 < 16; i0 += 8) {
-            u64 key[8], cur[8];
-            u32 hh[8], cnt[8];
-            bool lead[8];
+        for (int u = 0; u < 16; ++u) {
+            if (keys[u] == 0ull || keys[u] == pend_key) { old[u] = keys[u]; if (keys[u]) hh[u] = pend_h; }      // no row / slot known
+            else old[u] = atomicCAS(&hk[hh[u]], 0ull, keys[u]);
+        }
+        u32 restm = 0u;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                key[u] = (r0 + i0 + u < n) ? keys[i0 + u] + 1ull : 0ull;      // 0: no row
-                // (every row is its own leader: merging the lanes of one key with match.any first cost 4 400 cycles
-                // per match in the sampler -- 13.8 M of a 16.6 M-cycle scan -- and the tables of real cliques hold
-                // thousands of cells, the largest a few per cent of the rows; lanes that race for an empty slot with
-                // the same key all see it taken by that key, and only the winner lists the slot)
-                lead[u] = key[u] != 0ull;
-                cnt[u] = 1u;
-                hh[u] = (u32)((key[u] * 0x9E3779B97F4A7C15ull) >> 32) & hmask;      // (Fibonacci hashing: one multiply)
-                if (lead[u] && key[u] == pend_key) { cur[u] = key[u]; hh[u] = pend_h; }      // its slot is known
-                else cur[u] = lead[u] ? __ldcg(&hk[hh[u]]) : 0ull;
+        for (int u = 0; u < 16; ++u) {
+            if (keys[u] == 0ull) continue;
+            if (old[u] == 0ull) mylist[nlist++] = (int)hh[u];
+            else if (old[u] != keys[u]) { restm |= 1u << u; continue; }
+            if (keys[u] == pend_key) ++pend_cnt;
+            else {
+                if (pend_cnt) atomicAdd(&hc[pend_h], pend_cnt);
+                pend_key = keys[u]; pend_h = hh[u]; pend_cnt = 1u;
             }
-            // second wave: the leaders that saw an empty slot try to take it -- all compare-and-swaps of the
-            // batch in flight together
-            u64 old[8];
+        }
+        // linear probing, every unresolved row of the lane one step per round
+        while (__any_sync(PDG_FULL, restm != 0u)) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) old[u] = (lead[u] && cur[u] == 0ull) ? atomicCAS(&hk[hh[u]], 0ull, key[u]) : cur[u];
-            int nfresh = 0;
-            u32 freshm = 0u, hitm = 0u;
+            for (int u = 0; u < 16; ++u)
+                if ((restm >> u) & 1u) { hh[u] = (hh[u] + 1u) & hmask; old[u] = atomicCAS(&hk[hh[u]], 0ull, keys[u]); }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const bool fresh = lead[u] && cur[u] == 0ull && old[u] == 0ull;
-                const bool hit = lead[u] && (fresh || old[u] == key[u]);
-                freshm |= (u32)fresh << u; hitm |= (u32)hit << u;
-                nfresh += fresh ? 1 : 0;
-            }
-            // new cells are listed with ONE counter update per batch (warp prefix over the lanes' counts)
-            int incl = nfresh;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(PDG_FULL, incl, o); if (lane >= o) incl += v; }
-            const int total = __shfl_sync(PDG_FULL, incl, 31);
-            if (total) {
-                int lbase = 0;
-                if (lane == 31) lbase = atomicAdd(&list[0], total);
-                lbase = __shfl_sync(PDG_FULL, lbase, 31) + incl - nfresh;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) if ((freshm >> u) & 1u) list[1 + lbase++] = (int)hh[u];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (!((hitm >> u) & 1u)) continue;
-                if (key[u] == pend_key) pend_cnt += cnt[u];
-                else {
-                    if (pend_cnt) atomicAdd(&hc[pend_h], pend_cnt);
-                    pend_key = key[u]; pend_h = hh[u]; pend_cnt = cnt[u];
-                }
-            }
-            // the rest met another key in their slot: linear probing, one at a time (rare at this load factor)
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (!lead[u] || ((hitm >> u) & 1u)) continue;
-                u32 h = (hh[u] + 1) & hmask;
-                u64 c2 = __ldcg(&hk[h]);
-                for (;;) {
-                    if (c2 == 0ull) {
-                        c2 = atomicCAS(&hk[h], 0ull, key[u]);
-                        if (c2 == 0ull) list[1 + atomicAdd(&list[0], 1)] = (int)h;      // a new cell: remember its slot
-                    }
-                    if (c2 == 0ull || c2 == key[u]) { atomicAdd(&hc[h], cnt[u]); break; }
-                    h = (h + 1) & hmask;
-                    c2 = __ldcg(&hk[h]);
-                }
+            for (int u = 0; u < 16; ++u) {
+                if (!((restm >> u) & 1u)) continue;
+                if (old[u] == 0ull) mylist[nlist++] = (int)hh[u];
+                else if (old[u] != keys[u]) continue;
+                atomicAdd(&hc[hh[u]], 1u);
+                restm &= ~(1u << u);
             }
         }
         SPT(1)
@@ -649,14 +617,15 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     if (pend_cnt) atomicAdd(&hc[pend_h], pend_cnt);
     __threadfence();
     __syncwarp();
-    // the occupied slots come off the list (a few thousand cells), not off a pass over the whole table
-    const int ncell = *(volatile int *)&list[0];
+    // the occupied slots come off the lanes' lists (a few thousand cells), not off a pass over the whole table
+    const int ncell = (int)__reduce_add_sync(PDG_FULL, (unsigned int)nlist);
+    const int nlmax = (int)__reduce_max_sync(PDG_FULL, (unsigned int)nlist);
     unsigned int maxc = 0;
-    for (int i0 = 0; i0 < ncell; i0 += 128) {
+    for (int i0 = 0; i0 < nlmax; i0 += 4) {
         int hx[4];
         unsigned int cx[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u + lane; hx[u] = i < ncell ? __ldcg(&list[1 + i]) : -1; }
+        for (int u = 0; u < 4; ++u) hx[u] = i0 + u < nlist ? mylist[i0 + u] : -1;
 #pragma unroll
         for (int u = 0; u < 4; ++u) cx[u] = hx[u] >= 0 ? __ldcg(&hc[hx[u]]) : 0u;
 #pragma unroll
@@ -671,7 +640,6 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     __threadfence();
     __syncwarp();
     SPT(2)
-    if (lane == 0) list[0] = 0;
     // count-of-counts in ascending count order (order-free sum), eight loads in flight per lane
     for (unsigned int c0 = 1; c0 <= maxc; c0 += 256) {
         unsigned int mx[8];

@@ -389,7 +389,7 @@ int launch_score_m(pdg_ctx *ctx, const u64 *d_bits, long long n_sets, double *d_
 // developer probe (PDG_PHASE_TIMERS builds only): scans and cycles by set size, see loglin_scan
 extern "C" int pdg_debug_loglin_sp(unsigned long long *out)
 {
-    return cudaMemcpyFromSymbol(out, g_sp, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -2;
+    return cudaMemcpyFromSymbol(out, g_sp, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
 }
 extern "C" int pdg_debug_loglin_kh(unsigned long long *out)
 {

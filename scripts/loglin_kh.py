@@ -30,7 +30,7 @@ for k in range(32):
     if cnt[k]:
         print("%2d %9d  %.4f  %12.0f  %.4f" % (k, cnt[k], cnt[k] / cnt.sum(), cyc[k] / cnt[k], cyc[k] / tot))
 print("total scans (2 runs)", cnt.sum(), "scan cycles per warp per run", tot / 2 / w["chains"])
-sp = (C.c_uint64 * 8)()
+sp = (C.c_uint64 * 16)()
 if nat.lib().pdg_debug_loglin_sp(sp) == 0 and sp[4]:
     ns = float(sp[4])
     print("hashed-cell scans: %d; cycles per scan: keys %.0f, insertion %.0f, list pass %.0f, count-of-counts %.0f, wait for a pool %.0f; "
