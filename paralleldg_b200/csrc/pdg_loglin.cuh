@@ -201,6 +201,40 @@ __device__ __forceinline__ double ll_table_score(const LlConst &C, const unsigne
     return warp_sum(acc) - C.constK;
 }
 
+// Sum over a count table in global memory (cells dealt to lanes, ascending, like ll_table_score; the butterfly
+// is left to the caller) that also restores the all-zero state of the table.  A table of 2^16 cells is 256 KB
+// that has usually left L2 since this warp last used it: one dependent load per round trip made the sweep
+// 1.4 M cycles of a 2.3 M-cycle scan, so sixteen rounds of loads are in flight.  `pad`: rows of zero padding
+// that were counted into cell 0.
+static __device__ __noinline__ double ll_sweep_global(const LlConst C, unsigned int *tab, unsigned int ncell, unsigned int pad, int lane)
+{
+    double acc = 0.0;
+    constexpr int UB = 16;
+    if (C.LG) {
+        for (unsigned int c0 = 0u; c0 < ncell; c0 += 32u * UB) {
+            unsigned int cn[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) { const unsigned int c = c0 + 32u * u + lane; cn[u] = c < ncell ? __ldcg(&tab[c]) : 0u; }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) if (cn[u]) tab[c0 + 32u * u + lane] = 0u;
+            if (c0 == 0u && lane == 0) cn[0] -= pad;
+            double t[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) t[u] = cn[u] ? __ldg(&C.LG[cn[u]]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < UB; ++u) if (cn[u]) acc += t[u];
+        }
+    } else {
+        for (unsigned int c = lane; c < ncell; c += 32u) {
+            unsigned int cnt = __ldcg(&tab[c]);
+            if (cnt) tab[c] = 0u;
+            if (c == 0u) cnt -= pad;
+            if (cnt) acc += lgamma((double)cnt + C.alpha) - C.lga;
+        }
+    }
+    return acc;
+}
+
 // What the last dense scan left behind: when `cells` > 0 the exact count table of the set whose
 // sorted column list is still in ws.idx sits compact in shared memory at sh[0 .. cells).
 struct LlTable { unsigned int cells; int k; };
@@ -438,33 +472,7 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
         } else {
             __threadfence();
             __syncwarp();
-            // (a table of 2^16 cells is 256 KB that has usually left L2 since this warp last used it: one
-            // dependent load per round trip made this sweep 1.4 M cycles of a 2.3 M-cycle scan, so sixteen
-            // rounds of loads are in flight; cells stay dealt to lanes and are summed in ascending order)
-            constexpr int UB = 16;
-            const unsigned int ncell = (unsigned int)Ki;
-            if (C.LG) {
-                for (unsigned int c0 = 0u; c0 < ncell; c0 += 32u * UB) {
-                    unsigned int cn[UB];
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) { const unsigned int c = c0 + 32u * u + lane; cn[u] = c < ncell ? __ldcg(&hist[c]) : 0u; }
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) if (cn[u]) hist[c0 + 32u * u + lane] = 0u;
-                    if (c0 == 0u && lane == 0) cn[0] -= (unsigned int)(P.ld - n);
-                    double t[UB];
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) t[u] = cn[u] ? __ldg(&C.LG[cn[u]]) : 0.0;
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) if (cn[u]) acc += t[u];
-                }
-            } else {
-                for (unsigned int c = lane; c < ncell; c += 32u) {
-                    unsigned int cnt = __ldcg(&hist[c]);
-                    if (cnt) hist[c] = 0u;
-                    if (c == 0u) cnt -= (unsigned int)(P.ld - n);
-                    if (cnt) acc += lgamma((double)cnt + C.alpha) - C.lga;
-                }
-            }
+            acc = ll_sweep_global(C, hist, (unsigned int)Ki, (unsigned int)(P.ld - n), lane);
             __threadfence();
             __syncwarp();
             score = warp_sum(acc) - C.constK;
@@ -531,6 +539,12 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     G = __shfl_sync(PDG_FULL, G, 0);
     __syncwarp();
     if (G > 8) { if (lane == 0) atomicExch(&S.lock[s], 0); res.err = ERR_BIGCLIQUE; return res; }
+    // Tables that fit the pool's key array taken as 32-bit counters (2 * hslots cells: 17-19 binary columns at
+    // n = 10^5) are counted DENSELY there -- one fire-and-forget reduction per row on the mixed-radix code,
+    // then the sweep of the global dense path; a hashed insertion is a compare-and-swap whose result the
+    // warp waits for plus a reduction per row (8.7 M cycles per scan in the sampler).
+    const bool pool_dense = !big && Ki <= 2ull * (u64)S.hslots;
+    unsigned int *ptab = (unsigned int *)hk;
     // a lane that leads the same key again and again (the table's heaviest cell, as a rule) keeps that cell's
     // count in registers and adds it once: repeated reductions on one address were most of the insertion time
     u64 pend_key = 0ull;
@@ -569,6 +583,11 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
             for (int i = 0; i < 16; ++i) keys[i] = keys[i] * Kg + (u64)((cw[i >> 2] >> (8 * (i & 3))) & 0xffu);
         }
         SPT(0)
+        if (pool_dense) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) if (r0 + u < n) atomicAdd(&ptab[(u32)keys[u]], 1u);
+            continue;
+        }
         // All sixteen rows of the lane in ONE wave of compare-and-swaps: an empty slot is taken (a new cell: the
         // lane notes the slot in its own list), a slot holding the key is a hit, anything else walks on.  The
         // tables of real cliques hold thousands of thinly filled cells, so nearly every batch of rows opens new
@@ -617,6 +636,22 @@ __device__ __forceinline__ ScoreRes loglin_scan(LoglinArgs P, WarpScratch ws, in
     if (pend_cnt) atomicAdd(&hc[pend_h], pend_cnt);
     __threadfence();
     __syncwarp();
+    if (pool_dense) {
+        acc = ll_sweep_global(C, ptab, (unsigned int)Ki, 0u, lane);
+        __threadfence();
+        __syncwarp();
+        SPT(1)
+#ifdef PDG_PHASE_TIMERS
+        if (lane == 0) atomicAdd(&g_sp[4], 1ull);
+#endif
+        if (lane == 0) atomicExch(&S.lock[s], 0);
+        res.score = warp_sum(acc) - constK;
+#ifdef PDG_PHASE_TIMERS
+        if (lane == 0) { atomicAdd(&g_kh[0][k < 31 ? k : 31], 1ull); atomicAdd(&g_kh[1][k < 31 ? k : 31], (unsigned long long)(clock64() - kh_t0)); }
+        if (lane == 0) atomicAdd(&P.work[(size_t)slot * 16 + 15], (unsigned long long)(clock64() - kh_t0));
+#endif
+        return res;
+    }
     // the occupied slots come off the lanes' lists (a few thousand cells), not off a pass over the whole table
     const int ncell = (int)__reduce_add_sync(PDG_FULL, (unsigned int)nlist);
     const int nlmax = (int)__reduce_max_sync(PDG_FULL, (unsigned int)nlist);
